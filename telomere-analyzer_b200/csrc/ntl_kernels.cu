@@ -1,0 +1,631 @@
+/*
+ * ntl_kernels.cu -- sm_100a kernels of libnanotel_b200 other than the JIT-specialised scan:
+ *   K2  ntl_scan_kernel<2|4>   runtime-pattern build of ntl_scan.cuh (any pattern set; 4-plane build for IUPAC reads)
+ *   K4  ntl_filter_kernel      --use_filter edge filter            (filter_reads/filter_density, NanoTel.R:2083-2163)
+ *   K3  ntl_locate_kernel      per-read locator and refinement     (find_telo_position_wraper NanoTel.R:1080-1155 and
+ *                              everything it calls, analyze_read's densities and keep rule :1840-1868)
+ *
+ * K3/K4 are one warp per read with warp-uniform control flow; lanes evaluate 32 alignments / 32 windows at a time.
+ * They re-derive hits locally from the packed read where the reference consults its range list, so that K2 never
+ * has to spill per-base masks to HBM.  All fp64 expressions are written exactly as NanoTel.R evaluates them
+ * (int/int divisions in double, sums in window order); this file must be compiled with --fmad=false.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ntl_dev.h"
+#include "../../include/nanotel_b200.h"
+
+__constant__ ntl_dev_params c_prm;
+
+#include "ntl_scan.cuh"
+
+/* =============================================================================================================
+ * K2 (runtime-pattern build)
+ * ============================================================================================================= */
+template <int NPL>
+__global__ void __launch_bounds__(256) ntl_scan_kernel(const ntl_scan_args a)
+{
+    ntl_scan_body<NPL>(a);
+}
+
+/* =============================================================================================================
+ * Shared by K3 and K4: random access into a packed read
+ * ============================================================================================================= */
+struct ReadView {
+    const u32 *base;
+    int L;
+    int fmt;        /* 0: 2-bit quads of 8 words, 1: 4-bit quads of 16 words */
+    int n_words;
+};
+
+__device__ __forceinline__ u32 rv_word(const ReadView &rv, int plane, int w)
+{
+    if (w < 0 || w >= rv.n_words) return 0u;
+    const int q = w >> 2, i = w & 3;
+    return rv.fmt ? rv.base[(size_t)q * 16 + plane * 4 + i] : rv.base[(size_t)q * 8 + plane * 4 + i];
+}
+
+/* One-hot (ACGT reads) or IUPAC (4-bit reads) planes A, C, G, T for the 32 positions p .. p+31, zeroed outside
+ * [vlo, vhi].  A zero nibble matches nothing under both comparison rules, i.e. counts as a mismatch -- Biostrings'
+ * treatment of out-of-bounds letters (App. B.3). */
+__device__ __forceinline__ void rv_fetch4(const ReadView &rv, int p, int vlo, int vhi, u32 (&pl)[4])
+{
+    const int w = p >> 5, s = p & 31;
+    int lowb = vlo - p; if (lowb < 0) lowb = 0;
+    int highb = vhi - p; if (highb > 31) highb = 31;
+    u32 vm = 0u;
+    if (highb >= lowb) vm = (NTL_FULL >> (31 - highb)) & (NTL_FULL << lowb);
+    if (rv.fmt == 0) {
+        const u32 lo = __funnelshift_r(rv_word(rv, 0, w), rv_word(rv, 0, w + 1), s);
+        const u32 hi = __funnelshift_r(rv_word(rv, 1, w), rv_word(rv, 1, w + 1), s);
+        pl[0] = ~hi & ~lo & vm;     /* A = 0 */
+        pl[1] = ~hi & lo & vm;      /* C = 1 */
+        pl[2] = hi & lo & vm;       /* G = 3 */
+        pl[3] = hi & ~lo & vm;      /* T = 2 */
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            pl[k] = __funnelshift_r(rv_word(rv, k, w), rv_word(rv, k, w + 1), s) & vm;
+    }
+}
+
+/* mismatches of the alignment whose first letter sits on bit 0 of pl[] */
+__device__ __forceinline__ int pat_mismatches(const ntl_dev_pat &pt, bool fixed, const u32 (&pl)[4])
+{
+    const u32 mm = (1u << pt.m) - 1u;
+    u32 eq;
+    if (fixed) eq = ~((pl[0] ^ pt.q4[0]) | (pl[1] ^ pt.q4[1]) | (pl[2] ^ pt.q4[2]) | (pl[3] ^ pt.q4[3]));
+    else eq = (pl[0] & pt.q4[0]) | (pl[1] & pt.q4[1]) | (pl[2] & pt.q4[2]) | (pl[3] & pt.q4[3]);
+    return __popc(~eq & mm);
+}
+
+/* Hit-start bits for alignment starts p0 .. p0+31 of one pattern (Biostrings::matchPattern, App. B.2/B.3):
+ * positions outside [vlo, vhi] are mismatches.  mode_fixed < 0: use the pattern's own fixed flag. */
+__device__ __forceinline__ u32 hits32(const ReadView &rv, const ntl_dev_pat &pt, int k, int mode_fixed, int p0, int vlo,
+                                      int vhi, int lane)
+{
+    u32 pl[4];
+    rv_fetch4(rv, p0 + lane, vlo, vhi, pl);
+    const bool fx = mode_fixed < 0 ? (pt.fixed != 0) : (mode_fixed != 0);
+    return __ballot_sync(NTL_FULL, pat_mismatches(pt, fx, pl) <= k);
+}
+
+/* Coverage bits of track t (0 exact, 1 one mismatch, 2 one mismatch + TVR) for positions p0 .. p0+31: the union of
+ * the trimmed hit intervals of get_density_iranges (NanoTel.R:308-397). */
+__device__ u32 cov_word(const ReadView &rv, int t, int p0, int lane)
+{
+    u32 cov = 0u;
+    const int k = t >= 1 ? 1 : 0;
+    for (int p = 0; p < c_prm.n_main; p++) {
+        const ntl_dev_pat &pt = c_prm.main_pat[p];
+        const u32 h0 = hits32(rv, pt, k, -1, p0 - 32, 1, rv.L, lane);
+        const u32 h1 = hits32(rv, pt, k, -1, p0, 1, rv.L, lane);
+        const unsigned long long H = ((unsigned long long)h1 << 32) | h0;
+        unsigned long long D = H;
+        for (int j = 1; j < pt.m; j++) D |= H << j;
+        cov |= (u32)(D >> 32);
+    }
+    if (t == 2) {
+        for (int p = 0; p < c_prm.n_tvr; p++) {
+            const ntl_dev_pat &pt = c_prm.tvr_pat[p];
+            const u32 h0 = hits32(rv, pt, 0, -1, p0 - 32, 1, rv.L, lane);
+            const u32 h1 = hits32(rv, pt, 0, -1, p0, 1, rv.L, lane);
+            const unsigned long long H = ((unsigned long long)h1 << 32) | h0;
+            unsigned long long D = H;
+            for (int j = 1; j < pt.m; j++) D |= H << j;
+            cov |= (u32)(D >> 32);
+        }
+    }
+    /* trim() to [1, L] */
+    int lowb = 1 - p0; if (lowb < 0) lowb = 0;
+    int highb = rv.L - p0; if (highb > 31) highb = 31;
+    u32 vm = 0u;
+    if (highb >= lowb) vm = (NTL_FULL >> (31 - highb)) & (NTL_FULL << lowb);
+    return cov & vm;
+}
+
+/* covered positions of track t inside [lo, hi] (1 <= lo, hi <= L), recomputed from the read */
+__device__ int local_count(const ReadView &rv, int t, int lo, int hi, int lane)
+{
+    int total = 0;
+    for (int p0 = lo; p0 <= hi; p0 += 32) {
+        u32 w = cov_word(rv, t, p0, lane);
+        const int rem = hi - p0;
+        if (rem < 31) w &= NTL_FULL >> (31 - rem);
+        total += __popc(w);
+    }
+    return total;
+}
+
+/* =============================================================================================================
+ * K4: edge filter (filter_reads / filter_density, NanoTel.R:2083-2163)
+ * ============================================================================================================= */
+__global__ void __launch_bounds__(256) ntl_filter_kernel(const ntl_read_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= a.n_reads) return;
+    ReadView rv;
+    rv.L = a.len[r]; rv.fmt = a.fmt[r]; rv.base = a.packed + a.woff[r]; rv.n_words = (rv.L >> 5) + 1;
+    int keep = 0;
+    if (rv.L >= 1000) {                                         /* :2124 */
+        int lo, hi;
+        if (c_prm.right_edge) { hi = rv.L - 70; lo = hi - 199; }   /* subseq(end = -(70+1), width = 200) :2131-2134 */
+        else { lo = 71; hi = 270; }                                 /* subseq(start = 71, width = 200)   :2136       */
+        int covered = 0;
+        u32 hprev[NTL_DEV_MAX_PAT];
+        for (int p = 0; p < c_prm.n_main; p++) hprev[p] = 0u;
+        for (int p0 = lo; p0 <= hi; p0 += 32) {
+            u32 cov = 0u;
+            for (int p = 0; p < c_prm.n_main; p++) {                /* fixed = FALSE always, exact (:2091-2096) */
+                const ntl_dev_pat &pt = c_prm.main_pat[p];
+                const u32 h1 = hits32(rv, pt, 0, 0, p0, lo, hi, lane);
+                const unsigned long long H = ((unsigned long long)h1 << 32) | hprev[p];
+                unsigned long long D = H;
+                for (int j = 1; j < pt.m; j++) D |= H << j;
+                cov |= (u32)(D >> 32);
+                hprev[p] = h1;
+            }
+            const int rem = hi - p0;
+            if (rem < 31) cov &= NTL_FULL >> (31 - rem);
+            covered += __popc(cov);
+        }
+        const double total_density = (double)covered / (double)(hi - lo + 1);   /* :2100 */
+        keep = total_density >= c_prm.filter_threshold ? 1 : 0;                  /* :2101, :2143 */
+    }
+    if (lane == 0) a.pass[r] = (uint8_t)keep;
+}
+
+/* =============================================================================================================
+ * K3: locator
+ * ============================================================================================================= */
+struct WinTab {                 /* the window table of one track (analyze_subtelos :737-764), never materialised */
+    const uint16_t *cum;
+    int n, S, L;
+    double min_density;
+};
+__device__ __forceinline__ int wt_start(const WinTab &w, int k) { return 1 + k * w.S; }
+__device__ __forceinline__ int wt_end(const WinTab &w, int k) { return k == w.n - 1 ? w.L : (k + 1) * w.S; }
+__device__ __forceinline__ int wt_count(const WinTab &w, int k)
+{
+    const u32 hi = w.cum[k], lo = k > 0 ? (u32)w.cum[k - 1] : 0u;
+    return (int)((hi - lo) & 0xffffu);
+}
+__device__ __forceinline__ double wt_density(const WinTab &w, int k)
+{
+    return (double)wt_count(w, k) / (double)(wt_end(w, k) - wt_start(w, k) + 1);      /* :467 */
+}
+__device__ __forceinline__ bool wt_telo(const WinTab &w, int k)
+{
+    return !(wt_density(w, k) < w.min_density);                                         /* :751-758 */
+}
+
+/* The run/score machine of find_telo_position (NanoTel.R:1003-1025 forward, :1046-1068 backward) over windows
+ * i0, i0+dir, ..., i1 (0-based, inclusive).  Returns the window index at which  in_a_row >= R && score >= T  first
+ * holds, or -1; *first = first window of the run that is open when the scan stops (-1 if none). */
+__device__ int run_scan(const WinTab &w, int i0, int i1, int dir, double R, double T, int *first, int lane)
+{
+    double score = 0.0;
+    int run_first = -1, in_a_row = 0;
+    const int total = (i1 - i0) * dir + 1;
+    for (int done = 0; done < total; done += 32) {
+        const int idx = i0 + dir * (done + lane);
+        const bool valid = done + lane < total;
+        double d = 0.0;
+        bool tel = false;
+        if (valid) { d = wt_density(w, idx); tel = !(d < w.min_density); }
+        const u32 mask = __ballot_sync(NTL_FULL, tel);
+        const int nvalid = total - done < 32 ? total - done : 32;
+        int b = 0;
+        while (b < nvalid) {
+            if (!((mask >> b) & 1u)) {
+                score = 0.0; run_first = -1; in_a_row = 0;
+                const u32 rest = mask >> b;
+                if (rest == 0u) break;
+                b += __ffs((int)rest) - 1;
+                continue;
+            }
+            in_a_row += 1;
+            score = score + __shfl_sync(NTL_FULL, d, b);
+            if (run_first == -1) run_first = i0 + dir * (done + b);
+            if ((double)in_a_row >= R && score >= T) { *first = run_first; return i0 + dir * (done + b); }
+            b += 1;
+        }
+    }
+    *first = run_first;
+    return -1;
+}
+
+/* find_telo_position (NanoTel.R:973-1077) */
+__device__ void find_telo_position(const WinTab &w, double R, double T, int *ps, int *pe, int lane)
+{
+    const int n = w.n;
+    int first = -1;
+    int hit = n > 0 ? run_scan(w, 0, n - 1, +1, R, T, &first, lane) : -1;
+    if (hit < 0) { *ps = -1; *pe = -1; return; }                         /* :1026-1028 */
+    const int start = wt_start(w, first);
+    const int end_position = hit + 2;                                    /* 1-based i + 1 (:1022) */
+    int end;
+    if ((double)end_position >= (double)n - R + 1.0) {                   /* :1037-1044 */
+        int i = n;                                                       /* 1-based */
+        while (i > end_position && !wt_telo(w, i - 1)) i -= 1;
+        end = wt_end(w, i - 1);
+    } else {                                                             /* :1046-1068 */
+        int bfirst = -1;
+        run_scan(w, n - 1, end_position - 1, -1, R, T, &bfirst, lane);
+        end = bfirst >= 0 ? wt_end(w, bfirst) : -1;
+    }
+    if (start > end) end = start + (wt_end(w, 0) - wt_start(w, 0));       /* :1072-1074 */
+    *ps = start; *pe = end;
+}
+
+/* find_left_telo (NanoTel.R:906-959) */
+__device__ void find_left_telo(const WinTab &w, int *ps, int *pe)
+{
+    int start = 1, end = 1, last_i = 0;
+    const int n = w.n;
+    for (int i = 0; i < n; i++) {
+        if (wt_start(w, i) > 200) { *ps = -1; *pe = -1; return; }
+        if (!wt_telo(w, i)) continue;
+        start = wt_start(w, i); last_i = i; break;
+    }
+    for (int i = last_i; i < n; i++) {
+        if (!wt_telo(w, i)) break;
+        end = wt_end(w, i);
+    }
+    if (start > end) end = start + (wt_end(w, last_i) - wt_start(w, last_i));
+    *ps = start; *pe = end;
+}
+
+/* find_right_telo (NanoTel.R:843-899); n == 0 is the caller's REF_ERROR case */
+__device__ void find_right_telo(const WinTab &w, int *ps, int *pe)
+{
+    int start = 1, end = 1, last_i = 0;
+    const int n = w.n;
+    for (int i = n - 1; i >= 0; i--) {
+        if (wt_end(w, i) < w.L - 200) { *ps = -1; *pe = -1; return; }
+        if (!wt_telo(w, i)) continue;
+        end = wt_end(w, i); last_i = i; break;
+    }
+    for (int i = last_i; i >= 0; i--) {
+        if (!wt_telo(w, i)) break;
+        start = wt_start(w, i); last_i = i;
+    }
+    if (start > end) end = start + (wt_end(w, last_i) - wt_start(w, last_i));
+    *ps = start; *pe = end;
+}
+
+/* covered bases of track t inside [a, b] (get_sub_density's numerator, NanoTel.R:467): whole windows come from
+ * K2's prefixes, partial windows are recomputed from the read. */
+__device__ int covered_in(const ReadView &rv, const WinTab &w, int t, int a, int b, int lane)
+{
+    const int lo = a < 1 ? 1 : a, hi = b > rv.L ? rv.L : b;
+    if (hi < lo) return 0;
+    if (w.n <= 0) return local_count(rv, t, lo, hi, lane);
+    int klo = (lo - 1) / w.S; if (klo > w.n - 1) klo = w.n - 1;
+    int khi = (hi - 1) / w.S; if (khi > w.n - 1) khi = w.n - 1;
+    if (klo == khi) {
+        if (lo == wt_start(w, klo) && hi == wt_end(w, klo)) return wt_count(w, klo);
+        return local_count(rv, t, lo, hi, lane);
+    }
+    int total = 0, kf = klo, kl = khi;
+    if (lo != wt_start(w, klo)) { total += local_count(rv, t, lo, wt_end(w, klo), lane); kf = klo + 1; }
+    if (hi != wt_end(w, khi)) { total += local_count(rv, t, wt_start(w, khi), hi, lane); kl = khi - 1; }
+    int part = 0;
+    for (int k = kf + lane; k <= kl; k += 32) part += wt_count(w, k);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(NTL_FULL, part, d);
+    return total + part;
+}
+
+__device__ __forceinline__ double density_of(const ReadView &rv, const WinTab &w, int t, int a, int b, int lane)
+{
+    return (double)covered_in(rv, w, t, a, b, lane) / (double)(b - a + 1);
+}
+
+/* Range starts / ends of `ranges` (raw exact hits of the single fixed pattern, or the reduced runs of the coverage,
+ * NanoTel.R:349-354 vs :341-345) inside a span of <= 8 words starting at position sp0. */
+struct SpanBits { u32 st[8]; u32 en[8]; u32 cov[8]; int sp0; int nw; };
+
+__device__ void build_span(const ReadView &rv, int t, int sp0, int nw, SpanBits &sb, int lane)
+{
+    sb.sp0 = sp0; sb.nw = nw;
+    u32 covw[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) covw[i] = 0u;
+    /* coverage for words -1 .. nw (one extra word on each side for the run-boundary tests) */
+#pragma unroll
+    for (int i = 0; i < 10; i++)
+        if (i < nw + 2) covw[i] = cov_word(rv, t, sp0 + 32 * (i - 1), lane);
+    const bool raw = (t == 0) && c_prm.raw_hits_A;
+    u32 hs[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) hs[i] = 0u;
+    if (raw) {
+        const ntl_dev_pat &pt = c_prm.main_pat[0];
+#pragma unroll
+        for (int i = 0; i < 10; i++)
+            if (i < nw + 1) hs[i] = hits32(rv, pt, 0, -1, sp0 + 32 * (i - 1), 1, rv.L, lane);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (i < nw) {
+            const u32 c = covw[i + 1], cp = covw[i], cn = covw[i + 2];
+            sb.cov[i] = c;
+            if (raw) {
+                sb.st[i] = hs[i + 1];
+                sb.en[i] = __funnelshift_l(hs[i], hs[i + 1], c_prm.main_pat[0].m - 1);
+            } else {
+                sb.st[i] = c & ~((c << 1) | (cp >> 31));
+                sb.en[i] = c & ~((c >> 1) | (cn << 31));
+            }
+        } else { sb.cov[i] = 0u; sb.st[i] = 0u; sb.en[i] = 0u; }
+    }
+}
+
+/* smallest / largest position with a set bit inside [lo, hi]; INT_MIN-like -999999999 if none */
+#define NTL_NONE (-999999999)
+__device__ int span_min(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (i >= nw) break;
+        const int p0 = sp0 + 32 * i;
+        int lb = lo - p0; if (lb < 0) lb = 0;
+        int hb = hi - p0; if (hb > 31) hb = 31;
+        if (hb < lb) continue;
+        const u32 m = bits[i] & (NTL_FULL >> (31 - hb)) & (NTL_FULL << lb);
+        if (m) return p0 + __ffs((int)m) - 1;
+    }
+    return NTL_NONE;
+}
+__device__ int span_max(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
+{
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        if (i >= nw) continue;
+        const int p0 = sp0 + 32 * i;
+        int lb = lo - p0; if (lb < 0) lb = 0;
+        int hb = hi - p0; if (hb > 31) hb = 31;
+        if (hb < lb) continue;
+        const u32 m = bits[i] & (NTL_FULL >> (31 - hb)) & (NTL_FULL << lb);
+        if (m) return p0 + 31 - __clz((int)m);
+    }
+    return NTL_NONE;
+}
+__device__ int span_popc(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
+{
+    int total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (i >= nw) break;
+        const int p0 = sp0 + 32 * i;
+        int lb = lo - p0; if (lb < 0) lb = 0;
+        int hb = hi - p0; if (hb > 31) hb = 31;
+        if (hb < lb) continue;
+        total += __popc(bits[i] & (NTL_FULL >> (31 - hb)) & (NTL_FULL << lb));
+    }
+    return total;
+}
+
+/* get_accurate_end (NanoTel.R:1692-1721) */
+__device__ int get_accurate_end(const ReadView &rv, int t, int telo_end, int lane)
+{
+    if (telo_end == -1) return -1;
+    SpanBits sb;
+    build_span(rv, t, telo_end - 99, 5, sb, lane);                      /* [e-99, e+60] covers [e-99, e+50] */
+    int e_index = telo_end;
+    int m1 = span_max(sb.en, sb.sp0, sb.nw, telo_end - 99, telo_end);
+    if (m1 != NTL_NONE) e_index = m1;
+    int m2 = span_max(sb.en, sb.sp0, sb.nw, telo_end + 1, telo_end + 50);
+    if (m2 != NTL_NONE) e_index = m2;
+    return e_index;
+}
+
+/* get_accurate_start (NanoTel.R:1726-1764) */
+__device__ int get_accurate_start(const ReadView &rv, int t, int telo_start, int lane)
+{
+    if (telo_start == -1) return telo_start;
+    const int s = telo_start;
+    SpanBits sb;
+    build_span(rv, t, s - 36, 5, sb, lane);                             /* [s-36, s+123] covers [s-36, s+99] */
+    const int c50 = span_popc(sb.cov, sb.sp0, sb.nw, s, s + 49);
+    const double first_50 = (double)c50 / 50.0;                         /* IRanges(start, width = 50) :1732 */
+    if (first_50 < 0.3) {
+        int a = span_min(sb.st, sb.sp0, sb.nw, s + 48, s + 99);
+        if (a != NTL_NONE) telo_start = a;
+        int b = span_min(sb.st, sb.sp0, sb.nw, s + 33, s + 48);
+        if (b != NTL_NONE) telo_start = b;
+    } else {
+        int a = span_min(sb.st, sb.sp0, sb.nw, s, s + 99);
+        if (a != NTL_NONE) telo_start = a;
+        if (first_50 >= 0.72) {
+            int b = span_min(sb.st, sb.sp0, sb.nw, s - 36, s - 1);
+            if (b != NTL_NONE) telo_start = b;
+        }
+    }
+    return telo_start;
+}
+
+/* One 18-bp window of search_left/right_patterns (multi_pattern_step_*, NanoTel.R:496-575, :614, :676):
+ * matchPattern on subseq(read, a, b) with the default fixed = TRUE, the window's own out-of-bounds rule, hits not
+ * trimmed.  Returns false if no pattern hits. */
+__device__ bool step_window(const ReadView &rv, int a, int b, int k, bool use_tvr, int *min_start, int *max_end, int lane)
+{
+    bool any = false;
+    int mn = 0, mx = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        const int np = pass == 0 ? c_prm.n_main : (use_tvr ? c_prm.n_tvr : 0);
+        const int kk = pass == 0 ? k : 0;
+        for (int p = 0; p < np; p++) {
+            const ntl_dev_pat &pt = pass == 0 ? c_prm.main_pat[p] : c_prm.tvr_pat[p];
+            /* alignment starts a - kk .. b - m + 1 + kk : at most 18 - m + 1 + 2 <= 16 + 2 of them */
+            const int s0 = a - kk;
+            u32 h = hits32(rv, pt, kk, 1, s0, a, b, lane);
+            const int nstarts = (b - pt.m + 1 + kk) - s0 + 1;
+            if (nstarts <= 0) continue;
+            if (nstarts < 32) h &= (1u << nstarts) - 1u;
+            if (h) {
+                const int lo = s0 + __ffs((int)h) - 1;
+                const int hi = s0 + 31 - __clz((int)h) + pt.m - 1;
+                if (!any || lo < mn) mn = lo;
+                if (!any || hi > mx) mx = hi;
+                any = true;
+            }
+        }
+    }
+    *min_start = mn; *max_end = mx;
+    return any;
+}
+
+/* search_left_patterns (NanoTel.R:576-633) */
+__device__ int search_left(const ReadView &rv, int start_index, int k, bool use_tvr, int lane)
+{
+    int subseq_start = start_index - 18 > 1 ? start_index - 18 : 1;
+    int new_start = start_index;
+    for (int i = 0; i < 4; i++) {
+        const int curr_end = subseq_start + 17 < rv.L ? subseq_start + 17 : rv.L;
+        int mn, mx;
+        if (!step_window(rv, subseq_start, curr_end, k, use_tvr, &mn, &mx, lane)) break;
+        new_start = mn;
+        const int nn = subseq_start - 9 > 1 ? subseq_start - 9 : 1;
+        if (nn == subseq_start) break;
+        subseq_start = nn;
+    }
+    return new_start;
+}
+
+/* search_right_patterns (NanoTel.R:635-697) */
+__device__ int search_right(const ReadView &rv, int end_index, int k, bool use_tvr, int lane)
+{
+    int subseq_end = end_index + 18 < rv.L ? end_index + 18 : rv.L;
+    int new_end = end_index;
+    for (int i = 0; i < 4; i++) {
+        const int curr_start = subseq_end - 17 > 1 ? subseq_end - 17 : 1;
+        int mn, mx;
+        if (!step_window(rv, curr_start, subseq_end, k, use_tvr, &mn, &mx, lane)) break;
+        new_end = mx;
+        const int nn = subseq_end + 11 < rv.L ? subseq_end + 11 : rv.L;
+        if (nn == subseq_end) break;
+        subseq_end = nn;
+    }
+    return new_end;
+}
+
+__global__ void __launch_bounds__(128) ntl_locate_kernel(const ntl_read_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= a.n_reads) return;
+    ntl_read_result *res = reinterpret_cast<ntl_read_result *>(a.results) + r;
+    ntl_stage *stg = a.stages ? reinterpret_cast<ntl_stage *>(a.stages) + (size_t)r * 3 : nullptr;
+
+    ReadView rv;
+    rv.L = a.len[r]; rv.fmt = a.fmt[r]; rv.base = a.packed + a.woff[r]; rv.n_words = (rv.L >> 5) + 1;
+    const int S = c_prm.S, T = c_prm.n_tracks;
+    const int n_win = ntl_nwin(rv.L, S);
+    int status = rv.fmt ? NTL_READ_IUPAC : 0;
+    if (n_win <= 0) status |= NTL_READ_NO_WINDOWS;
+
+    ntl_track out[3];
+    for (int t = 0; t < 3; t++) { out[t].start = 0; out[t].end = 0; out[t].density = 0.0; }
+
+    if (a.pass != nullptr && a.pass[r] == 0) {
+        status |= NTL_READ_FILTERED;
+    } else {
+        bool err = false;
+        int max_width = 0;
+        for (int t = 0; t < T && !err; t++) {
+            WinTab w;
+            w.cum = a.cum[t] + a.win_off[r]; w.n = n_win > 0 ? n_win : 0; w.S = S; w.L = rv.L;
+            w.min_density = c_prm.min_density;
+            const int k = t >= 1 ? 1 : 0;
+            const bool use_tvr = t == 2;
+
+            int ts, te;
+            find_telo_position(w, 3.0, 2.0, &ts, &te, lane);                               /* :1084-1086 */
+            const double telo_density = density_of(rv, w, t, ts, te, lane);                /* :1099 */
+            const int num_rows = (te - ts + 1) / S;                                        /* :1103 */
+            if (telo_density < 0.85 && num_rows > 5) {                                     /* :1104-1110 */
+                const double min_rows = num_rows <= 7 ? (double)(num_rows - 2) : 7.0;
+                const double min_score = 0.6 * min_rows;
+                find_telo_position(w, min_rows, min_score, &ts, &te, lane);
+            }
+            const int cs = ts, ce = te;
+            int start_acc = get_accurate_start(rv, t, ts, lane);                           /* :1119 */
+            int end_acc = get_accurate_end(rv, t, te, lane);                               /* :1120 */
+            if (start_acc > end_acc) end_acc = start_acc;                                  /* :1122-1124 */
+            ts = start_acc; te = end_acc;
+            const int as = ts, ae = te;
+            double acc_density = 0.0;
+            if (stg) acc_density = density_of(rv, w, t, ts, te, lane);
+            if (te - ts + 1 < 100) {                                                       /* :1129-1136 */
+                if (c_prm.right_edge) {
+                    if (w.n == 0) { err = true; break; }                                   /* R stops at :859-861 */
+                    find_right_telo(w, &ts, &te);
+                } else find_left_telo(w, &ts, &te);
+            }
+            if (stg && lane == 0) {
+                ntl_stage s;
+                s.coarse_start = cs; s.coarse_end = ce; s.acc_start = as; s.acc_end = ae;
+                s.edge_start = ts; s.edge_end = te; s.acc_density = acc_density;
+                stg[t] = s;
+            }
+            int e2, s2;
+            if (te < rv.L) e2 = search_right(rv, te + 1, k, use_tvr, lane);                /* :1140-1144 */
+            else e2 = te;
+            if (ts > 1) s2 = search_left(rv, ts - 1, k, use_tvr, lane);                    /* :1145-1149 */
+            else s2 = ts;
+            if (e2 < s2 - 1) { err = true; break; }                                        /* IRanges() would stop */
+            out[t].start = s2; out[t].end = e2;
+            out[t].density = density_of(rv, w, t, s2, e2, lane);                           /* :1840-1844 */
+            const int wd = e2 - s2 + 1;
+            if (wd > max_width) max_width = wd;
+        }
+        if (err) status |= NTL_READ_REF_ERROR;
+        else if (max_width >= 30) status |= NTL_READ_KEEP;                                 /* :1847, :1857 */
+    }
+    if (lane == 0) {
+        res->status = status;
+        res->n_win = n_win > 0 ? n_win : 0;
+        for (int t = 0; t < 3; t++) res->track[t] = out[t];
+        res->win_offset = a.win_off[r];
+    }
+}
+
+/* =============================================================================================================
+ * launchers (called from ntl_api.cpp)
+ * ============================================================================================================= */
+extern "C" cudaError_t ntl_k_set_params(const ntl_dev_params *p, cudaStream_t st)
+{
+    return cudaMemcpyToSymbolAsync(c_prm, p, sizeof(ntl_dev_params), 0, cudaMemcpyHostToDevice, st);
+}
+
+extern "C" cudaError_t ntl_k_scan(const ntl_scan_args *a, int four_bit, int grid, cudaStream_t st)
+{
+    if (a->n_items <= 0) return cudaSuccess;
+    if (four_bit) ntl_scan_kernel<4><<<grid, 256, 0, st>>>(*a);
+    else ntl_scan_kernel<2><<<grid, 256, 0, st>>>(*a);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t ntl_k_scan_occupancy(int *blocks_per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ntl_scan_kernel<2>, 256, 0);
+}
+
+extern "C" cudaError_t ntl_k_filter(const ntl_read_args *a, cudaStream_t st)
+{
+    if (a->n_reads <= 0) return cudaSuccess;
+    const int wpb = 8;
+    ntl_filter_kernel<<<(a->n_reads + wpb - 1) / wpb, wpb * 32, 0, st>>>(*a);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t ntl_k_locate(const ntl_read_args *a, cudaStream_t st)
+{
+    if (a->n_reads <= 0) return cudaSuccess;
+    const int wpb = 4;
+    ntl_locate_kernel<<<(a->n_reads + wpb - 1) / wpb, wpb * 32, 0, st>>>(*a);
+    return cudaGetLastError();
+}

@@ -1,0 +1,186 @@
+/*
+ * ntl_pack.cpp -- host side of the boundary: ASCII reads -> planar bit streams in pinned memory.
+ *
+ * Replaces, for the GPU path, what Biostrings does when readDNAStringSet() encodes letters and when
+ * reverseComplement() is applied to the chunk (NanoTel.R:2213, 2219-2221): --rc is folded into the packer, so all
+ * coordinates the kernels produce are already in the reverse-complemented frame, as in the reference.
+ * Layout: see ntl_dev.h.  AVX2 path: 32 letters -> two movemasks (bit 1 and bit 2 of the ASCII code are the 2-bit
+ * code of A/C/G/T in either case); scalar path otherwise.
+ */
+#include "ntl_pack.h"
+#include <string.h>
+#include <atomic>
+#include <thread>
+#include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+/* Biostrings DNA codes, low nibble only (gap letters - + . have no base bit). 0xFF = not DNA. */
+static uint8_t g_nib[256];
+static uint8_t g_is_acgt[256];
+static bool g_tables = false;
+
+static void init_tables()
+{
+    if (g_tables) return;
+    memset(g_nib, 0xFF, sizeof g_nib);
+    memset(g_is_acgt, 0, sizeof g_is_acgt);
+    const char *letters = "ACGTMRWSYKVHDBN";
+    const uint8_t codes[] = {1, 2, 4, 8, 3, 5, 9, 6, 10, 12, 7, 11, 13, 14, 15};
+    for (int i = 0; letters[i]; i++) {
+        g_nib[(unsigned char)letters[i]] = codes[i];
+        g_nib[(unsigned char)(letters[i] | 0x20)] = codes[i];
+    }
+    g_nib[(unsigned char)'-'] = 0; g_nib[(unsigned char)'+'] = 0; g_nib[(unsigned char)'.'] = 0;
+    const char *acgt = "ACGTacgt";
+    for (int i = 0; acgt[i]; i++) g_is_acgt[(unsigned char)acgt[i]] = 1;
+    g_tables = true;
+}
+
+int ntl_pattern_nibble(char c)
+{
+    init_tables();
+    uint8_t n = g_nib[(unsigned char)c];
+    if (n == 0xFF || n == 0) return -1;     /* gap letters are not accepted in patterns */
+    return n;
+}
+
+static inline uint8_t comp_nib(uint8_t n)   /* A<->T, C<->G: reverse the 4 bits */
+{
+    return (uint8_t)(((n & 1) << 3) | ((n & 2) << 1) | ((n & 4) >> 1) | ((n & 8) >> 3));
+}
+
+/* 32 letters starting at base index b0 (0-based, in the OUTPUT frame) -> lo/hi masks; returns false if a letter is
+ * not A/C/G/T.  n <= 32 letters are valid, the rest of the masks is zero. */
+static inline bool block_scalar(const char *s, int64_t L, int rc, int64_t b0, int n, uint32_t *lo, uint32_t *hi)
+{
+    uint32_t l = 0, h = 0;
+    for (int i = 0; i < n; i++) {
+        unsigned char c = rc ? (unsigned char)s[L - 1 - (b0 + i)] : (unsigned char)s[b0 + i];
+        if (!g_is_acgt[c]) return false;
+        uint32_t code = (c >> 1) & 3u;
+        if (rc) code ^= 2u;
+        l |= (code & 1u) << i;
+        h |= (code >> 1) << i;
+    }
+    *lo = l; *hi = h;
+    return true;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2")))
+static inline bool block_avx2(const char *s, int64_t L, int rc, int64_t b0, uint32_t *lo, uint32_t *hi)
+{
+    __m256i v;
+    if (rc) {
+        v = _mm256_loadu_si256((const __m256i *)(s + (L - 32 - b0)));
+        const __m256i rev = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0,
+                                             15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+        v = _mm256_shuffle_epi8(v, rev);
+        v = _mm256_permute2x128_si256(v, v, 0x01);
+    } else {
+        v = _mm256_loadu_si256((const __m256i *)(s + b0));
+    }
+    const __m256i u = _mm256_or_si256(v, _mm256_set1_epi8(0x20));
+    __m256i ok = _mm256_cmpeq_epi8(u, _mm256_set1_epi8('a'));
+    ok = _mm256_or_si256(ok, _mm256_cmpeq_epi8(u, _mm256_set1_epi8('c')));
+    ok = _mm256_or_si256(ok, _mm256_cmpeq_epi8(u, _mm256_set1_epi8('g')));
+    ok = _mm256_or_si256(ok, _mm256_cmpeq_epi8(u, _mm256_set1_epi8('t')));
+    if (_mm256_movemask_epi8(ok) != -1) return false;
+    uint32_t l = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));   /* ASCII bit 1 -> code bit 0 */
+    uint32_t h = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));   /* ASCII bit 2 -> code bit 1 */
+    if (rc) h = ~h;
+    *lo = l; *hi = h;
+    return true;
+}
+#endif
+
+static bool g_have_avx2 =
+#if defined(__x86_64__)
+    __builtin_cpu_supports("avx2");
+#else
+    false;
+#endif
+
+static inline void put_word(uint32_t *dst, int words_per_quad, int plane, int64_t w, uint32_t val)
+{
+    dst[(w >> 2) * words_per_quad + plane * 4 + (w & 3)] = val;
+}
+
+int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst)
+{
+    init_tables();
+    const int64_t n_words = (L >> 5) + 1;
+    const int64_t n_quads = (n_words + 3) >> 2;
+    const int64_t n_blocks = (L + 31) >> 5;          /* unshifted 32-letter blocks */
+    uint32_t carry_lo = 0, carry_hi = 0;             /* bit 31 of the previous block -> bit 0 of the next word */
+    int64_t k = 0;
+    for (; k < n_blocks; k++) {
+        uint32_t lo, hi;
+        const int64_t b0 = k << 5;
+        const int n = L - b0 >= 32 ? 32 : (int)(L - b0);
+        bool ok;
+#if defined(__x86_64__)
+        if (n == 32 && g_have_avx2) ok = block_avx2(s, L, rc, b0, &lo, &hi);
+        else
+#endif
+            ok = block_scalar(s, L, rc, b0, n, &lo, &hi);
+        if (!ok) return 1;
+        /* position p = b0 + i + 1 lives at bit index p: shift the block up by one bit */
+        put_word(dst, 8, 0, k, (lo << 1) | carry_lo);
+        put_word(dst, 8, 1, k, (hi << 1) | carry_hi);
+        carry_lo = lo >> 31; carry_hi = hi >> 31;
+    }
+    /* remaining words of the last quad (the word holding only the carried bit, then zero padding) */
+    for (int64_t w = k; w < n_quads * 4; w++) {
+        put_word(dst, 8, 0, w, carry_lo);
+        put_word(dst, 8, 1, w, carry_hi);
+        carry_lo = carry_hi = 0;
+    }
+    return 0;
+}
+
+int ntl_pack_read_4bit(const char *s, int64_t L, int rc, uint32_t *dst)
+{
+    init_tables();
+    const int64_t n_words = (L >> 5) + 1;
+    const int64_t n_quads = (n_words + 3) >> 2;
+    memset(dst, 0, (size_t)n_quads * 16 * sizeof(uint32_t));
+    for (int64_t p = 1; p <= L; p++) {
+        unsigned char c = rc ? (unsigned char)s[L - p] : (unsigned char)s[p - 1];
+        uint8_t nb = g_nib[c];
+        if (nb == 0xFF) return -1;
+        if (rc) nb = comp_nib(nb);
+        const int64_t w = p >> 5;
+        const uint32_t bit = 1u << (p & 31);
+        uint32_t *q = dst + (w >> 2) * 16 + (w & 3);
+        if (nb & 1) q[0] |= bit;
+        if (nb & 2) q[4] |= bit;
+        if (nb & 4) q[8] |= bit;
+        if (nb & 8) q[12] |= bit;
+    }
+    return 0;
+}
+
+void ntl_parallel_for(int64_t n, int n_threads, int64_t grain, const std::function<void(int64_t, int64_t)> &fn)
+{
+    if (n <= 0) return;
+    if (n_threads <= 1 || n <= grain) { fn(0, n); return; }
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            int64_t b = next.fetch_add(grain);
+            if (b >= n) break;
+            int64_t e = b + grain < n ? b + grain : n;
+            fn(b, e);
+        }
+    };
+    std::vector<std::thread> th;
+    int nt = n_threads;
+    if ((int64_t)nt > (n + grain - 1) / grain) nt = (int)((n + grain - 1) / grain);
+    th.reserve(nt);
+    for (int t = 1; t < nt; t++) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+}

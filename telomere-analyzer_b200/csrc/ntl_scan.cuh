@@ -1,0 +1,377 @@
+/*
+ * ntl_scan.cuh -- K2, the streaming kernel of the hot path (sm_100a).
+ *
+ * For every read it produces, in ONE pass over the packed bases, what NanoTel.R computes with
+ *   get_density_iranges (NanoTel.R:308-397)  -> pattern hits (exact / <=1 mismatch / +TVR) and their union,
+ *   split_telo          (NanoTel.R:199-227)  -> the window table,
+ *   get_sub_density     (NanoTel.R:449-468)  -> covered bases per window (numerator of the density),
+ * for tracks A (exact), B (<= 1 mismatch) and C (B + exact TVR patterns).
+ *
+ * Mapping to the machine (B200: 148 SMs, 32-wide warps, LDG.256, 64-lane/clk integer pipe):
+ *   - one warp streams one read, longest reads first (dynamic work counter), 4096 positions per step:
+ *     lane l owns 128 consecutive positions = one 32-byte quad {lo[4], hi[4]}, fetched with one LDG.256
+ *     (1 KiB per warp per step, fully coalesced); the next step's quad is prefetched into registers;
+ *   - matching is Shift-And in its position-parallel form: one 32-bit word holds 32 text positions, a pattern
+ *     letter is one boolean function of the two bit-planes (LOP3), its j-th letter is aligned with a funnel
+ *     shift, and mismatches are counted in a 2-bit bit-sliced saturating counter (ones/twos):
+ *         exact hit  = ~(ones | twos)         (track A)
+ *         <=1 hit    = ~twos                  (track B)
+ *     positions outside [1, L] carry an all-zero "equal" mask, which reproduces Biostrings' rule that
+ *     out-of-bounds letters are mismatches (hits may start at 0 or end at L+1 with one mismatch, App. B.3);
+ *   - coverage (IRanges::union of the hit intervals, then trim) = hit-start mask dilated by the pattern length
+ *     with log-step funnel shifts; the <= 17 bits that spill into the next lane travel by one shuffle;
+ *   - window counts: per-lane popcounts, one packed warp scan per step, and every window end that falls into a
+ *     lane's 128 positions is written by that lane as the running prefix "covered bases in [1, window end]"
+ *     (uint16, mod 2^16).  Each prefix is written exactly once: no atomics, no zero-fill.  Consumers take
+ *     differences.
+ *
+ * Compiled twice from this one source: by nvcc with the patterns in __constant__ memory (any pattern set), and by
+ * NVRTC at ntl_create() with the pattern set baked in (NTL_JIT), which turns every pattern letter into a single
+ * LOP3 and fully unrolls the letter loops.
+ */
+#ifndef NTL_SCAN_CUH
+#define NTL_SCAN_CUH
+
+#include "ntl_dev.h"
+
+typedef unsigned int u32;
+
+#ifndef NTL_JIT
+/* c_prm (__constant__ ntl_dev_params) is defined by the including .cu file before this header */
+#define PRM_S        (c_prm.S)
+#define PRM_NTRACKS  (c_prm.n_tracks)
+#define PRM_NMAIN    (c_prm.n_main)
+#define PRM_NTVR     (c_prm.n_tvr)
+#define PRM_MAIN_LEN(p) (c_prm.main_pat[p].m)
+#define PRM_TVR_LEN(p)  (c_prm.tvr_pat[p].m)
+#define PRM_NMAIN_GROUPS (c_prm.n_main_groups)
+#define PRM_NTVR_GROUPS  (c_prm.n_tvr_groups)
+#define PRM_MAIN_GBEGIN(g) (c_prm.main_group_begin[g])
+#define PRM_TVR_GBEGIN(g)  (c_prm.tvr_group_begin[g])
+#define NTL_UNROLL_PAT _Pragma("unroll 1")
+#define NTL_UNROLL_LET _Pragma("unroll 1")
+#else
+#define PRM_S        NTL_J_S
+#define PRM_NTRACKS  NTL_J_NTRACKS
+#define PRM_NMAIN    NTL_J_NMAIN
+#define PRM_NTVR     NTL_J_NTVR
+#define PRM_MAIN_LEN(p) (NTL_J_MAIN_LEN[p])
+#define PRM_TVR_LEN(p)  (NTL_J_TVR_LEN[p])
+#define PRM_NMAIN_GROUPS NTL_J_NMAIN_GROUPS
+#define PRM_NTVR_GROUPS  NTL_J_NTVR_GROUPS
+#define PRM_MAIN_GBEGIN(g) (NTL_J_MAIN_GBEGIN[g])
+#define PRM_TVR_GBEGIN(g)  (NTL_J_TVR_GBEGIN[g])
+#define NTL_UNROLL_PAT _Pragma("unroll")
+#define NTL_UNROLL_LET _Pragma("unroll")
+#endif
+
+#define NTL_FULL 0xffffffffu
+
+__device__ __forceinline__ int ntl_nwin(int L, int S)
+{
+    /* split_telo, NanoTel.R:216-224: drop the last window if  L - last_start < S / 2  (real division) */
+    int n = (L - 1) / S + 1;
+    int last = 1 + (n - 1) * S;
+    if (2 * (L - last) < S) n -= 1;
+    return n;
+}
+
+__device__ __forceinline__ void ntl_ldg256(const u32 *p, u32 (&v)[8])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+
+/* bits b of the word starting at bit index wpos with 1 <= wpos + b <= L */
+__device__ __forceinline__ u32 ntl_valid_word(int wpos, int L)
+{
+    int rem = L - wpos;
+    u32 m = rem >= 31 ? NTL_FULL : (rem < 0 ? 0u : ((2u << rem) - 1u));
+    if (wpos == 0) m &= ~1u;
+    return m;
+}
+
+/* "letter accepts this base" over 32 positions of a 2-bit read; t[c] = all-ones iff code c (= hi*2+lo) accepted */
+__device__ __forceinline__ u32 ntl_eq2(u32 hi, u32 lo, u32 v, u32 t0, u32 t1, u32 t2, u32 t3)
+{
+    u32 a = (lo & t1) | (~lo & t0);
+    u32 b = (lo & t3) | (~lo & t2);
+    return ((hi & b) | (~hi & a)) & v;
+}
+
+/* Dilate hit starts forward by m positions, in place, over 5 words (word 4 receives the spill of word 3). */
+__device__ __forceinline__ void ntl_dilate5(u32 (&d)[5], int m)
+{
+    int w = 1;
+    while (2 * w <= m) {
+#pragma unroll
+        for (int i = 4; i >= 1; i--) d[i] |= __funnelshift_l(d[i - 1], d[i], w);
+        d[0] |= d[0] << w;
+        w *= 2;
+    }
+    int s = m - w;
+    if (s > 0) {
+#pragma unroll
+        for (int i = 4; i >= 1; i--) d[i] |= __funnelshift_l(d[i - 1], d[i], s);
+        d[0] |= d[0] << s;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * NPL = 2: ACGT reads, planes {lo, hi};  NPL = 4: IUPAC reads, planes {A, C, G, T} (Biostrings code bits).
+ * ------------------------------------------------------------------------------------------------------------ */
+template <int NPL>
+__device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int lane, int kq_init, int off_init,
+                                              int adv_a, int adv_b)
+{
+    const int S = PRM_S;
+    const int T = PRM_NTRACKS;
+    const int L = a.len[r];
+    const int n_win = ntl_nwin(L, S);
+    if (n_win <= 0) return;
+    const u32 *base = a.packed + a.woff[r];
+    const long long wo = a.win_off[r];
+    const int n_words = (L >> 5) + 1;
+    const int n_quads = (n_words + 3) >> 2;
+    const int n_chunks = (n_quads + 31) >> 5;
+    constexpr int QW = NPL * 4;                    /* words per quad */
+
+    u32 carry[3] = {0u, 0u, 0u};                   /* coverage spill of the previous chunk's lane 31 -> lane 0 */
+    u32 run[3] = {0u, 0u, 0u};                     /* covered bases before this chunk (warp-uniform)          */
+    int kq = kq_init, off = off_init;              /* first multiple of S at or after this lane's first bit   */
+
+    u32 cur[QW], nxt[QW];
+#pragma unroll
+    for (int i = 0; i < QW; i++) cur[i] = 0u;
+    if (lane < n_quads) {
+        if constexpr (NPL == 2) ntl_ldg256(base + (size_t)lane * 8, *reinterpret_cast<u32(*)[8]>(&cur[0]));
+        else {
+            ntl_ldg256(base + (size_t)lane * 16, *reinterpret_cast<u32(*)[8]>(&cur[0]));
+            ntl_ldg256(base + (size_t)lane * 16 + 8, *reinterpret_cast<u32(*)[8]>(&cur[8]));
+        }
+    }
+
+    for (int c = 0; c < n_chunks; c++) {
+        /* ---- prefetch the next chunk's quad */
+        const int qn = (c + 1) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < QW; i++) nxt[i] = 0u;
+        if (qn < n_quads) {
+            if constexpr (NPL == 2) ntl_ldg256(base + (size_t)qn * 8, *reinterpret_cast<u32(*)[8]>(&nxt[0]));
+            else {
+                ntl_ldg256(base + (size_t)qn * 16, *reinterpret_cast<u32(*)[8]>(&nxt[0]));
+                ntl_ldg256(base + (size_t)qn * 16 + 8, *reinterpret_cast<u32(*)[8]>(&nxt[8]));
+            }
+        }
+
+        /* ---- planes: 4 own words + the first word of the next lane (next chunk for lane 31) */
+        u32 pl[NPL][5];
+#pragma unroll
+        for (int k = 0; k < NPL; k++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) pl[k][i] = cur[k * 4 + i];
+            u32 nb = __shfl_sync(NTL_FULL, cur[k * 4], (lane + 1) & 31);
+            u32 nc = __shfl_sync(NTL_FULL, nxt[k * 4], 0);
+            pl[k][4] = lane == 31 ? nc : nb;
+        }
+        const int pos0 = (c * 32 + lane) * NTL_LANE_BITS;      /* bit index = 1-based position */
+        u32 v[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) v[i] = ntl_valid_word(pos0 + 32 * i, L);
+
+        u32 cov[3][5];
+#pragma unroll
+        for (int t = 0; t < 3; t++)
+#pragma unroll
+            for (int i = 0; i < 5; i++) cov[t][i] = 0u;
+
+        /* ---- main patterns: tracks A and B (get_density_iranges :327-356) */
+        {
+            NTL_UNROLL_PAT
+            for (int g = 0; g < PRM_NMAIN_GROUPS; g++) {
+                const int m = PRM_MAIN_LEN(PRM_MAIN_GBEGIN(g));
+                u32 hA[5] = {0u, 0u, 0u, 0u, 0u}, hB[5] = {0u, 0u, 0u, 0u, 0u};
+                NTL_UNROLL_PAT
+                for (int p = PRM_MAIN_GBEGIN(g); p < PRM_MAIN_GBEGIN(g + 1); p++) {
+                    u32 ones[4] = {0u, 0u, 0u, 0u}, twos[4] = {0u, 0u, 0u, 0u};
+                    NTL_UNROLL_LET
+                    for (int j = 0; j < m; j++) {
+                        u32 e[5];
+#ifndef NTL_JIT
+                        if constexpr (NPL == 2) {
+                            const u32 t0 = c_prm.main_pat[p].mux2[j][0], t1 = c_prm.main_pat[p].mux2[j][1];
+                            const u32 t2 = c_prm.main_pat[p].mux2[j][2], t3 = c_prm.main_pat[p].mux2[j][3];
+#pragma unroll
+                            for (int i = 0; i < 5; i++) e[i] = ntl_eq2(pl[NPL - 1][i], pl[0][i], v[i], t0, t1, t2, t3);
+                        } else {
+                            const u32 nb = c_prm.main_pat[p].nib[j];
+                            const u32 mA = (nb & 1u) ? NTL_FULL : 0u, mC = (nb & 2u) ? NTL_FULL : 0u;
+                            const u32 mG = (nb & 4u) ? NTL_FULL : 0u, mT = (nb & 8u) ? NTL_FULL : 0u;
+                            const bool fx = c_prm.main_pat[p].fixed != 0;
+#pragma unroll
+                            for (int i = 0; i < 5; i++) {
+                                u32 any = (pl[0][i] & mA) | (pl[1][i] & mC) | (pl[2][i] & mG) | (pl[3][i] & mT);
+                                u32 dif = (pl[0][i] ^ mA) | (pl[1][i] ^ mC) | (pl[2][i] ^ mG) | (pl[3][i] ^ mT);
+                                e[i] = (fx ? ~dif : any) & v[i];
+                            }
+                        }
+#else
+#pragma unroll
+                        for (int i = 0; i < 5; i++) e[i] = ntl_jit_eq_main(p, j, pl[NPL - 1][i], pl[0][i], v[i]);
+#endif
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            u32 x = ~__funnelshift_r(e[i], e[i + 1], j);
+                            twos[i] |= ones[i] & x;
+                            ones[i] ^= x;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { hA[i] |= ~(ones[i] | twos[i]); hB[i] |= ~twos[i]; }
+                }
+                ntl_dilate5(hA, m);
+                ntl_dilate5(hB, m);
+#pragma unroll
+                for (int i = 0; i < 5; i++) { cov[0][i] |= hA[i]; cov[1][i] |= hB[i]; }
+            }
+        }
+        /* ---- TVR patterns, exact: track C = B + TVR (get_density_iranges :360-393) */
+        if (T == 3) {
+            NTL_UNROLL_PAT
+            for (int g = 0; g < PRM_NTVR_GROUPS; g++) {
+                const int m = PRM_TVR_LEN(PRM_TVR_GBEGIN(g));
+                u32 hC[5] = {0u, 0u, 0u, 0u, 0u};
+                NTL_UNROLL_PAT
+                for (int p = PRM_TVR_GBEGIN(g); p < PRM_TVR_GBEGIN(g + 1); p++) {
+                    u32 mis[4] = {0u, 0u, 0u, 0u};
+                    NTL_UNROLL_LET
+                    for (int j = 0; j < m; j++) {
+                        u32 e[5];
+#ifndef NTL_JIT
+                        if constexpr (NPL == 2) {
+                            const u32 t0 = c_prm.tvr_pat[p].mux2[j][0], t1 = c_prm.tvr_pat[p].mux2[j][1];
+                            const u32 t2 = c_prm.tvr_pat[p].mux2[j][2], t3 = c_prm.tvr_pat[p].mux2[j][3];
+#pragma unroll
+                            for (int i = 0; i < 5; i++) e[i] = ntl_eq2(pl[NPL - 1][i], pl[0][i], v[i], t0, t1, t2, t3);
+                        } else {
+                            const u32 nb = c_prm.tvr_pat[p].nib[j];
+                            const u32 mA = (nb & 1u) ? NTL_FULL : 0u, mC = (nb & 2u) ? NTL_FULL : 0u;
+                            const u32 mG = (nb & 4u) ? NTL_FULL : 0u, mT = (nb & 8u) ? NTL_FULL : 0u;
+                            const bool fx = c_prm.tvr_pat[p].fixed != 0;
+#pragma unroll
+                            for (int i = 0; i < 5; i++) {
+                                u32 any = (pl[0][i] & mA) | (pl[1][i] & mC) | (pl[2][i] & mG) | (pl[3][i] & mT);
+                                u32 dif = (pl[0][i] ^ mA) | (pl[1][i] ^ mC) | (pl[2][i] ^ mG) | (pl[3][i] ^ mT);
+                                e[i] = (fx ? ~dif : any) & v[i];
+                            }
+                        }
+#else
+#pragma unroll
+                        for (int i = 0; i < 5; i++) e[i] = ntl_jit_eq_tvr(p, j, pl[NPL - 1][i], pl[0][i], v[i]);
+#endif
+#pragma unroll
+                        for (int i = 0; i < 4; i++) mis[i] |= ~__funnelshift_r(e[i], e[i + 1], j);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) hC[i] |= ~mis[i];
+                }
+                ntl_dilate5(hC, m);
+#pragma unroll
+                for (int i = 0; i < 5; i++) cov[2][i] |= hC[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 5; i++) cov[2][i] |= cov[1][i];
+        }
+
+        /* ---- coverage spill from the previous lane, trim to [1, L], popcounts */
+        u32 pc[3][4], tot[3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            if (t < T) {
+                u32 sp = __shfl_up_sync(NTL_FULL, cov[t][4], 1);
+                if (lane == 0) sp = carry[t];
+                carry[t] = __shfl_sync(NTL_FULL, cov[t][4], 31);
+                cov[t][0] |= sp;
+                tot[t] = 0u;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    cov[t][i] &= v[i];
+                    pc[t][i] = (u32)__popc(cov[t][i]);
+                    tot[t] += pc[t][i];
+                }
+            } else {
+                tot[t] = 0u;
+#pragma unroll
+                for (int i = 0; i < 4; i++) pc[t][i] = 0u;
+            }
+        }
+        /* ---- packed warp scan: (A | B << 16) and C; each lane total <= 128, chunk total <= 4096 */
+        u32 s01 = tot[0] | (tot[1] << 16), s2 = tot[2];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u32 y01 = __shfl_up_sync(NTL_FULL, s01, d);
+            u32 y2 = __shfl_up_sync(NTL_FULL, s2, d);
+            if (lane >= d) { s01 += y01; s2 += y2; }
+        }
+        u32 ex[3];
+        ex[0] = run[0] + (s01 & 0xffffu) - tot[0];
+        ex[1] = run[1] + (s01 >> 16) - tot[1];
+        ex[2] = run[2] + s2 - tot[2];
+        {
+            u32 l01 = __shfl_sync(NTL_FULL, s01, 31), l2 = __shfl_sync(NTL_FULL, s2, 31);
+            run[0] += l01 & 0xffffu; run[1] += l01 >> 16; run[2] += l2;
+        }
+
+        /* ---- window ends inside this lane's 128 positions: regular ends at multiples of S (index kq-1, only
+         *      kq <= n_win-1), and the last window's end at L (index n_win-1; split_telo :218, :223) */
+        {
+            int o = off, k = kq;
+            const int rel_last = L - pos0;
+            bool do_last = rel_last >= 0 && rel_last < NTL_LANE_BITS;
+            while (o < NTL_LANE_BITS || do_last) {
+                int rel, idx;
+                if (o < NTL_LANE_BITS) { rel = o; idx = k - 1; o += S; k += 1; if (idx < 0 || idx > n_win - 2) continue; }
+                else { rel = rel_last; idx = n_win - 1; do_last = false; }
+                const int wi = rel >> 5;
+                const u32 bm = NTL_FULL >> (31 - (rel & 31));
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    if (t < T) {
+                        u32 wv = wi == 0 ? cov[t][0] : wi == 1 ? cov[t][1] : wi == 2 ? cov[t][2] : cov[t][3];
+                        u32 bf = wi == 0 ? 0u : wi == 1 ? pc[t][0] : wi == 2 ? pc[t][0] + pc[t][1]
+                                                                            : pc[t][0] + pc[t][1] + pc[t][2];
+                        a.cum[t][wo + idx] = (uint16_t)(ex[t] + bf + (u32)__popc(wv & bm));
+                    }
+                }
+            }
+        }
+        /* ---- advance this lane's window-end cursor by one chunk (4096 = adv_a * S + adv_b) */
+        if (off >= adv_b) { off -= adv_b; kq += adv_a; }
+        else { off += S - adv_b; kq += adv_a + 1; }
+
+#pragma unroll
+        for (int i = 0; i < QW; i++) cur[i] = nxt[i];
+    }
+}
+
+template <int NPL>
+__device__ __forceinline__ void ntl_scan_body(const ntl_scan_args &a)
+{
+    const int lane = threadIdx.x & 31;
+    const int S = PRM_S;
+    const int kq_init = (NTL_LANE_BITS * lane + S - 1) / S;
+    const int off_init = kq_init * S - NTL_LANE_BITS * lane;
+    const int adv_a = NTL_CHUNK_BITS / S, adv_b = NTL_CHUNK_BITS % S;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(a.counter, 1u);
+        item = __shfl_sync(NTL_FULL, item, 0);
+        if (item >= a.n_items) break;
+        const int r = a.order[item];
+        if (a.pass != nullptr && a.pass[r] == 0) continue;
+        ntl_scan_read<NPL>(a, r, lane, kq_init, off_init, adv_a, adv_b);
+    }
+}
+
+#endif /* NTL_SCAN_CUH */

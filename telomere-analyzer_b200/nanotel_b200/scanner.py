@@ -1,0 +1,184 @@
+"""Scanner: a thin, typed wrapper over one ntl_ctx (one CUDA device, one NanoTel parameter set).
+
+It adds nothing to the C ABI except numpy views; all arithmetic happens in libnanotel_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+class NanoTelError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__("libnanotel_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class Scanner:
+    """One GPU context for a fixed (--patterns, --tvr_patterns, --min_density, --subseq_length, --rc,
+    --use_filter, --check_right_edge) set -- the arguments NanoTel.R fixes for a whole run (NanoTel.R:2322-2341)."""
+
+    def __init__(self, patterns, tvr_patterns=None, min_density: float = 0.6, subseq_length: int = 100,
+                 rc: bool = False, use_filter: bool = False, right_edge: bool = False, device: int = 0,
+                 jit: Optional[bool] = None, debug_stages: bool = False, host_threads: int = 0):
+        self._L = _lib.load()
+        options = 0
+        if jit is False:
+            options |= _lib.OPT_NO_JIT
+        elif jit is True:
+            options |= _lib.OPT_REQUIRE_JIT
+        if debug_stages:
+            options |= _lib.OPT_DEBUG_STAGES
+        self.params = _lib.make_params(patterns, tvr_patterns, min_density, subseq_length, rc, use_filter,
+                                       right_edge, device, options, host_threads)
+        self.n_tracks = 3 if self.params.n_tvr > 0 else 2
+        self.debug_stages = debug_stages
+        self._h = C.c_void_p()
+        rc_ = self._L.ntl_create(C.byref(self._h), C.byref(self.params))
+        if rc_ != _lib.NTL_OK:
+            msg = self._L.ntl_last_error(None).decode(errors="replace")
+            self._h = C.c_void_p()
+            raise NanoTelError(rc_, msg)
+        self._n = 0
+        self._keep = None
+
+    # -- lifecycle
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.ntl_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc != _lib.NTL_OK:
+            raise NanoTelError(rc, self._L.ntl_last_error(self._h).decode(errors="replace"))
+
+    @property
+    def note(self) -> str:
+        return self._L.ntl_last_error(self._h).decode(errors="replace")
+
+    # -- batches
+    @staticmethod
+    def _marshal(seqs: Sequence[bytes]):
+        n = len(seqs)
+        arr = (C.c_char_p * max(n, 1))(*seqs)
+        lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=n)
+        return arr, lens
+
+    def _results_view(self, ptr: C.c_void_p, n: int) -> np.ndarray:
+        if n == 0:
+            return np.zeros(0, _lib.RESULT_DTYPE)
+        buf = (C.c_char * (n * 64)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=_lib.RESULT_DTYPE, count=n)
+
+    def scan(self, seqs: Sequence[bytes]) -> np.ndarray:
+        """ntl_scan_batch: host ASCII reads in, one RESULT_DTYPE record per read out (a copy)."""
+        arr, lens = self._marshal(seqs)
+        self._keep = (arr, lens, seqs)
+        out = C.c_void_p()
+        self._check(self._L.ntl_scan_batch(self._h, arr, lens.ctypes.data, len(seqs), C.byref(out)))
+        self._n = len(seqs)
+        return self._results_view(out, self._n).copy()
+
+    @staticmethod
+    def _marshal_concat(buf: np.ndarray, offsets: np.ndarray):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        ptrs = (np.uint64(buf.ctypes.data) + offsets[:-1].astype(np.uint64)).astype(np.uint64)
+        lens = np.diff(offsets).astype(np.int64)
+        return buf, ptrs, lens
+
+    def scan_concat(self, buf: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        """Reads given as one ASCII buffer + offsets (read i = buf[offsets[i]:offsets[i+1]])."""
+        buf, ptrs, lens = self._marshal_concat(buf, offsets)
+        self._keep = (buf, ptrs, lens)
+        out = C.c_void_p()
+        self._check(self._L.ntl_scan_batch(self._h, ptrs.ctypes.data, lens.ctypes.data, len(lens), C.byref(out)))
+        self._n = len(lens)
+        return self._results_view(out, self._n).copy()
+
+    def pack_concat(self, buf: np.ndarray, offsets: np.ndarray) -> None:
+        buf, ptrs, lens = self._marshal_concat(buf, offsets)
+        self._keep = (buf, ptrs, lens)
+        self._check(self._L.ntl_batch_pack(self._h, ptrs.ctypes.data, lens.ctypes.data, len(lens)))
+        self._n = len(lens)
+
+    def pack(self, seqs: Sequence[bytes]) -> None:
+        arr, lens = self._marshal(seqs)
+        self._keep = (arr, lens, seqs)
+        self._check(self._L.ntl_batch_pack(self._h, arr, lens.ctypes.data, len(seqs)))
+        self._n = len(seqs)
+
+    def upload(self) -> None:
+        self._check(self._L.ntl_batch_upload(self._h))
+
+    def run(self) -> None:
+        self._check(self._L.ntl_batch_run(self._h))
+
+    def download(self) -> np.ndarray:
+        out = C.c_void_p()
+        self._check(self._L.ntl_batch_download(self._h, C.byref(out)))
+        return self._results_view(out, self._n).copy()
+
+    def timings(self) -> dict:
+        t = _lib.Timings()
+        self._check(self._L.ntl_get_timings(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in _lib.Timings._fields_}
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.ntl_stream(self._h) or 0)
+
+    # -- per-window tables (analyze_subtelos' data.frame, NanoTel.R:740-765)
+    def windows(self, read_idx: int, track: int, n_win: Optional[int] = None):
+        if n_win is None:
+            n_win = self._L.ntl_get_windows(self._h, read_idx, track, 0, None, None, None, None)
+            if n_win < 0:
+                self._check(n_win)
+        st = np.zeros(max(n_win, 1), np.int32)
+        en = np.zeros(max(n_win, 1), np.int32)
+        cov = np.zeros(max(n_win, 1), np.int32)
+        den = np.zeros(max(n_win, 1), np.float64)
+        r = self._L.ntl_get_windows(self._h, read_idx, track, n_win, st.ctypes.data, en.ctypes.data,
+                                    cov.ctypes.data, den.ctypes.data)
+        if r < 0:
+            self._check(r)
+        return st[:n_win], en[:n_win], cov[:n_win], den[:n_win]
+
+    def stages(self, read_idx: int, track: int) -> dict:
+        s = _lib.Stage()
+        self._check(self._L.ntl_get_stages(self._h, read_idx, track, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in _lib.Stage._fields_}
+
+
+def assign_serials(results: np.ndarray, serial_start: int = 1):
+    """ntl_assign_serials: (serial[n], row_order[rows], next_serial_start) -- NanoTel.R:2050-2069, 2234-2258."""
+    L = _lib.load()
+    res = np.ascontiguousarray(results, dtype=_lib.RESULT_DTYPE)
+    n = len(res)
+    serial = np.zeros(max(n, 1), np.int32)
+    order = np.zeros(max(n, 1), np.int32)
+    nxt = C.c_int32(serial_start)
+    rows = L.ntl_assign_serials(res.ctypes.data, n, serial_start, serial.ctypes.data, order.ctypes.data, C.byref(nxt))
+    if rows < 0:
+        raise NanoTelError(rows, "ntl_assign_serials")
+    return serial[:n], order[:rows], nxt.value
+
+
+def count_windows(length: int, subseq_length: int) -> int:
+    return _lib.load().ntl_count_windows(int(length), int(subseq_length))
