@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- Gbases/s scanned (telomere calls bit-exact) on N B200s, with the HBM roofline and a CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4] [--reads R]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (edge filter if enabled -> scan -> locate) over one batch of synthetic reads.
+Workload (BASELINE.json configs[1], "cfg2"): 100 000 synthetic ONT-like reads per GPU (median 20 kb, ~2.3 Gbases,
+10 % telomeric), --patterns YYAGGG --rc, seed 20261018 + 2 (+ rank).  Every rank scans its own shard (reads are
+independent: no collective; weak scaling), `value` = bases of all ranks / max-over-ranks device time.
+
+  value      kernels only, packed reads resident in HBM (575 MB per GPU > 126 MB L2, so every step streams from HBM)
+  e2e        ntl_scan_batch(): pageable host ASCII in -> host results out (pack to pinned, H2D, kernels, D2H inside)
+  roofline   scan kernel: algorithmic bytes (ceil(L*2/8) + T*n_win*2 + 64 per read) / CUDA-event time
+  cpu_baseline / --impl reference: the oracle (CPU restatement of NanoTel.R; R itself is not installable here)
+             on all host cores over a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "telomere-analyzer_b200"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (patterns, tvr, rc, use_filter, right_edge, S, description)
+    "cfg2": ("YYAGGG", None, True, False, False, 100,
+             "synthetic ONT-like reads (median 20 kb, 10% telomeric), --patterns YYAGGG --rc"),
+    "cfg3": ("YYAGGG", "TTGGG CCAGGG TCAGGG", True, False, False, 100,
+             "cfg2 + --tvr_patterns 'TTGGG CCAGGG TCAGGG' (3 tracks)"),
+    "cfg4": ("TTAGGG", None, False, True, True, 100,
+             "synthetic reads, --patterns TTAGGG --use_filter --check_right_edge"),
+}
+SEED = 20261018
+
+
+def algorithmic_bytes(lengths: np.ndarray, S: int, T: int) -> int:
+    """per read ceil(L*2/8) + T*n_win*2 + 64 (2-bit reads)."""
+    L = lengths.astype(np.int64)
+    n0 = (L - 1) // S + 1
+    last = 1 + (n0 - 1) * S
+    n_win = n0 - (2 * (L - last) < S)
+    return int(((L * 2 + 7) // 8).sum() + (T * n_win * 2).sum() + 64 * len(L))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self._stop.is_set():
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def ncu_traffic(workload: str):
+    """dram bytes per scan-kernel launch from the committed ncu --set full capture, if one exists for this workload."""
+    p = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+def cpu_baseline(buf, offsets, wl, n_sample: int, threads: int):
+    """The oracle on `threads` host cores over the first n_sample reads of the workload.  TEST INFRASTRUCTURE used
+    as the reported CPU baseline only."""
+    from oracle import oracle as O
+    patterns, tvr, rc, use_filter, right_edge, S, _ = wl
+    n = min(n_sample, len(offsets) - 1)
+    seqs = [buf[int(offsets[i]):int(offsets[i + 1])].tobytes() for i in range(n)]
+    bases = int(offsets[n] - offsets[0])
+    P = O.make_params(patterns, tvr, 0.6, S, right_edge)
+    t0 = time.perf_counter()
+    O.scan_batch(P, seqs, do_rc=rc, use_filter=use_filter, n_threads=threads, want_windows=False)
+    dt = time.perf_counter() - t0
+    return bases / dt / 1e9, bases, n, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=100000, help="reads per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=20000, help="reads of the CPU-baseline sample")
+    ap.add_argument("--no-jit", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    patterns, tvr, rc, use_filter, right_edge, S, desc = wl
+    T = 3 if tvr else 2
+    cores = os.cpu_count() or 1
+    config = {"workload": "%s: %d reads/GPU, %s" % (args.workload, args.reads, desc),
+              "reads_per_gpu": args.reads, "subseq_length": S, "min_density": 0.6, "tracks": T,
+              "l2_policy": "inputs larger than L2 (packed reads >> 126 MB); no flush", "seed": SEED + 2}
+
+    from nanotel_b200.synth import synth_reads
+
+    # ---------------------------------------------------------------- reference arm: CPU only, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_gen = min(args.reads, max(args.cpu_sample, 1000))
+        buf, offsets, meta = synth_reads(n_gen, SEED + 2)
+        vals = []
+        for it in range(args.warmup + args.steps):
+            v, bases, n, dt = cpu_baseline(buf, offsets, wl, args.cpu_sample, cores)
+            if it >= args.warmup:
+                vals.append((v, dt))
+        value = float(np.mean([v for v, _ in vals]))
+        ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+        sample = "first %d reads (%d bases) of the %s workload per step" % (n, bases, args.workload)
+        line = {"impl": "reference", "metric": "Gbases/s scanned (telomere calls bit-exact)", "value": value,
+                "unit": "Gbases/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32 bit-planes + f64 densities", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "Gbases/s", "cores": cores, "kind": "port", "sample": sample,
+                                 "note": "CPU restatement of NanoTel.R (oracle/), not the R/Biostrings path: R is "
+                                         "not installable in this image"},
+                "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libnanotel_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from nanotel_b200 import Scanner
+
+    buf, offsets, meta = synth_reads(args.reads, SEED + 2 + 1000 * rank)
+    bases = int(meta["bases"])
+    sc = Scanner(patterns, tvr, 0.6, S, rc=rc, use_filter=use_filter, right_edge=right_edge, device=local_rank,
+                 jit=False if args.no_jit else None)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # -- device-resident timing: pack + upload once, then K timed passes
+    sc.pack_concat(buf, offsets)
+    sc.upload()
+    for _ in range(max(args.warmup, 3)):
+        sc.run()
+    stream = torch.cuda.ExternalStream(sc.stream, device=torch.device("cuda", local_rank))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    ev0.record(stream)
+    done = 0
+    while done < args.steps:
+        k = min(256, args.steps - done)
+        for _ in range(k):
+            sc.enqueue()
+        if done + k >= args.steps:
+            ev1.record(stream)
+        sc.wait()
+        done += k
+        if done < args.steps:
+            tm_part = sc.timings()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    tm = sc.timings()
+    clocks = sampler.stop() if sampler else None
+    steps_cov = max(tm["steps"], 1)
+    scan_ms = tm["scan_ms"] / steps_cov
+    locate_ms = tm["locate_ms"] / steps_cov
+    filter_ms = tm["filter_ms"] / steps_cov
+    launches_per_step = tm["kernel_launches"] / steps_cov
+
+    # -- end to end through the public call, host buffers in and out
+    res = sc.scan_concat(buf, offsets)          # warm-up (allocations)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        res = sc.scan_concat(buf, offsets)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    tm_e2e = sc.timings()
+    n_keep = int((res["status"] & 1).sum())
+
+    # -- max over ranks
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+    b = torch.tensor([float(bases)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
+    total_bases = float(b[0])
+
+    if rank == 0:
+        ms_per_step = dev_ms_max / args.steps
+        value = total_bases / (ms_per_step * 1e-3) / 1e9
+        alg = algorithmic_bytes(meta["lengths"], S, T)
+        peak, peak_src = measured_peak_hbm()
+        achieved = alg / (scan_ms * 1e-3) / 1e9
+        line = {
+            "metric": "Gbases/s scanned (telomere calls bit-exact)", "value": value, "unit": "Gbases/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 bit-planes + f64 densities", "data": "synthetic", "config": config,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.workload), "kernel": "ntl_scan_jit" if tm["scan_is_jit"] else "ntl_scan_kernel<2>",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                         "bytes_per_base": alg / bases, "kernel_ms": scan_ms},
+            "kernel_ms": {"filter": filter_ms, "scan": scan_ms, "locate": locate_ms},
+            "e2e": {"value": total_bases / e2e_s_max / 1e9, "unit": "Gbases/s",
+                    "h2d_bytes_per_step": int(tm_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(tm_e2e["d2h_bytes"]),
+                    "ms_per_step": e2e_s_max * 1e3,
+                    "breakdown_ms": {k: tm_e2e[k] for k in ("pack_ms", "h2d_ms", "filter_ms", "scan_ms", "locate_ms", "d2h_ms")},
+                    "host_threads": min(cores, 64)},
+            "gpu_launches": int(round(launches_per_step * args.steps)),
+            "clocks": clocks, "telomeric_reads_found_rank0": n_keep, "bases_per_gpu": bases,
+        }
+        if not args.no_cpu_baseline:
+            v, sb, sn, dt = cpu_baseline(buf, offsets, wl, args.cpu_sample, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "Gbases/s", "cores": cores, "kind": "port",
+                                    "sample": "first %d reads (%d bases) of rank 0's shard, %.1f s" % (sn, sb, dt)}
+        print(json.dumps(line))
+    sc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -110,8 +110,10 @@ typedef struct {        /* wall/device times of the last batch, milliseconds */
     int64_t packed_bytes;   /* bytes of packed reads resident on the device                                  */
     int64_t window_bytes;   /* bytes of per-window prefix counts written by the scan kernel                  */
     int64_t h2d_bytes, d2h_bytes;
-    int32_t kernel_launches;/* kernels launched by the last ntl_batch_run                                    */
+    int32_t kernel_launches;/* kernels launched by the passes the last ntl_batch_wait covered                */
     int32_t scan_is_jit;    /* 1 if the NVRTC-specialised scan kernel ran                                    */
+    int32_t steps;          /* passes covered by filter_ms / scan_ms / locate_ms (sums over those passes)    */
+    int32_t reserved;
 } ntl_timings;
 
 typedef struct ntl_ctx ntl_ctx;
@@ -137,6 +139,8 @@ int ntl_scan_batch_concat(ntl_ctx *ctx, const char *buf, const int64_t *offsets,
 int ntl_batch_pack(ntl_ctx *ctx, const char *const *seq, const int64_t *len, int32_t n_reads);
 int ntl_batch_upload(ntl_ctx *ctx);       /* pinned host -> HBM (async on the context stream, then sync)  */
 int ntl_batch_run(ntl_ctx *ctx);          /* filter + scan + locate kernels on the resident batch, sync    */
+int ntl_batch_enqueue(ntl_ctx *ctx);      /* the same pass, enqueued on the context stream without waiting  */
+int ntl_batch_wait(ntl_ctx *ctx);         /* wait for the enqueued passes (<= 256); timings = sums over them */
 int ntl_batch_download(ntl_ctx *ctx, const ntl_read_result **results);
 int ntl_get_timings(const ntl_ctx *ctx, ntl_timings *out);
 void *ntl_stream(const ntl_ctx *ctx);     /* cudaStream_t the kernels are launched on */

@@ -64,6 +64,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+#define NTL_EVENT_RING 256
 enum { ST_EMPTY = 0, ST_PACKED = 1, ST_UPLOADED = 2, ST_RAN = 3, ST_DOWNLOADED = 4 };
 
 } // namespace
@@ -75,6 +76,8 @@ struct ntl_ctx {
     int device = 0, n_sms = 0, scan_grid = 0, host_threads = 1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr};
+    cudaEvent_t ring[NTL_EVENT_RING][4] = {{nullptr}};
+    int pending = 0, pending_launches = 0;
     char err[512] = "";
     ntl_jit_kernel *jit = nullptr;
 
@@ -300,6 +303,8 @@ extern "C" void ntl_destroy(ntl_ctx *c)
     c->d_packed.release(); c->d_meta.release(); c->d_results.release(); c->d_cum.release(); c->d_stages.release();
     c->d_pass.release(); c->d_counter.release();
     for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int k = 0; k < NTL_EVENT_RING; k++)
+        for (int i = 0; i < 4; i++) if (c->ring[k][i]) cudaEventDestroy(c->ring[k][i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -448,14 +453,20 @@ extern "C" int ntl_batch_upload(ntl_ctx *c)
 }
 
 /* ============================================================================================== run */
-extern "C" int ntl_batch_run(ntl_ctx *c)
+/* Enqueue one pass of the hot path (filter, scan, locate) on the context stream without waiting.  Event quads live
+ * in a ring so that a timed loop of back-to-back passes still yields per-kernel device times. */
+extern "C" int ntl_batch_enqueue(ntl_ctx *c)
 {
     if (!c) return NTL_ERR_ARG;
-    if (c->state < ST_UPLOADED) return fail(c, NTL_ERR_STATE, "ntl_batch_run before ntl_batch_upload");
+    if (c->state < ST_UPLOADED) return fail(c, NTL_ERR_STATE, "ntl_batch_enqueue before ntl_batch_upload");
     CK(c, cudaSetDevice(c->device));
+    if (c->pending >= NTL_EVENT_RING) return fail(c, NTL_ERR_STATE, "more than %d passes enqueued without ntl_batch_wait", NTL_EVENT_RING);
     const int32_t n = c->n_reads;
     const int T = c->dev.n_tracks;
     char *dm = (char *)c->d_meta.p;
+    cudaEvent_t *ev = c->ring[c->pending];
+    for (int i = 0; i < 4; i++)
+        if (!ev[i]) CK(c, cudaEventCreate(&ev[i]));
 
     ntl_read_args ra;
     memset(&ra, 0, sizeof ra);
@@ -478,9 +489,9 @@ extern "C" int ntl_batch_run(ntl_ctx *c)
 
     int launches = 0;
     CK(c, cudaMemsetAsync(c->d_counter.p, 0, 64, c->stream));
-    CK(c, cudaEventRecord(c->ev[2], c->stream));
+    CK(c, cudaEventRecord(ev[0], c->stream));
     if (c->dev.use_filter && n > 0) { CK(c, ntl_k_filter(&ra, c->stream)); launches++; }
-    CK(c, cudaEventRecord(c->ev[3], c->stream));
+    CK(c, cudaEventRecord(ev[1], c->stream));
     c->tm.scan_is_jit = 0;
     if (c->n2 > 0) {
         sa.order = (const int32_t *)(dm + c->off_order);
@@ -502,17 +513,43 @@ extern "C" int ntl_batch_run(ntl_ctx *c)
         CK(c, ntl_k_scan(&sa, 1, c->scan_grid, c->stream));
         launches++;
     }
-    CK(c, cudaEventRecord(c->ev[4], c->stream));
+    CK(c, cudaEventRecord(ev[2], c->stream));
     if (n > 0) { CK(c, ntl_k_locate(&ra, c->stream)); launches++; }
-    CK(c, cudaEventRecord(c->ev[5], c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
-    float ms = 0.f;
-    CK(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->tm.filter_ms = ms;
-    CK(c, cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->tm.scan_ms = ms;
-    CK(c, cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); c->tm.locate_ms = ms;
-    c->tm.kernel_launches = launches;
-    c->state = ST_RAN;
+    CK(c, cudaEventRecord(ev[3], c->stream));
+    c->pending_launches += launches;
+    c->pending++;
     return NTL_OK;
+}
+
+/* Wait for the enqueued passes; timings hold the SUMS over those passes, tm.steps their number. */
+extern "C" int ntl_batch_wait(ntl_ctx *c)
+{
+    if (!c) return NTL_ERR_ARG;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    double f = 0, s = 0, l = 0;
+    for (int k = 0; k < c->pending; k++) {
+        float ms = 0.f;
+        cudaEvent_t *ev = c->ring[k];
+        CK(c, cudaEventElapsedTime(&ms, ev[0], ev[1])); f += ms;
+        CK(c, cudaEventElapsedTime(&ms, ev[1], ev[2])); s += ms;
+        CK(c, cudaEventElapsedTime(&ms, ev[2], ev[3])); l += ms;
+    }
+    if (c->pending > 0) {
+        c->tm.filter_ms = f; c->tm.scan_ms = s; c->tm.locate_ms = l;
+        c->tm.steps = c->pending;
+        c->tm.kernel_launches = c->pending_launches;
+        c->state = ST_RAN;
+    }
+    c->pending = 0; c->pending_launches = 0;
+    return NTL_OK;
+}
+
+extern "C" int ntl_batch_run(ntl_ctx *c)
+{
+    int rc = ntl_batch_enqueue(c);
+    if (rc == NTL_OK) rc = ntl_batch_wait(c);
+    return rc;
 }
 
 /* ============================================================================================== download */

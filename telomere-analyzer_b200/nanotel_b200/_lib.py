@@ -37,7 +37,7 @@ class Timings(C.Structure):
         ("locate_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
         ("bases", C.c_int64), ("packed_bytes", C.c_int64), ("window_bytes", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-        ("kernel_launches", C.c_int32), ("scan_is_jit", C.c_int32),
+        ("kernel_launches", C.c_int32), ("scan_is_jit", C.c_int32), ("steps", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -55,7 +55,7 @@ assert RESULT_DTYPE.itemsize == 64
 # every symbol include/nanotel_b200.h declares
 EXPORTS = [
     "ntl_version", "ntl_create", "ntl_destroy", "ntl_last_error", "ntl_scan_batch", "ntl_scan_batch_concat",
-    "ntl_batch_pack", "ntl_batch_upload", "ntl_batch_run", "ntl_batch_download", "ntl_get_timings", "ntl_stream",
+    "ntl_batch_pack", "ntl_batch_upload", "ntl_batch_run", "ntl_batch_enqueue", "ntl_batch_wait", "ntl_batch_download", "ntl_get_timings", "ntl_stream",
     "ntl_get_windows", "ntl_get_stages", "ntl_jit_compile_check", "ntl_assign_serials", "ntl_count_windows",
 ]
 
@@ -84,6 +84,8 @@ def load() -> C.CDLL:
     L.ntl_batch_pack.argtypes = [vp, vp, vp, i32]
     L.ntl_batch_upload.argtypes = [vp]
     L.ntl_batch_run.argtypes = [vp]
+    L.ntl_batch_enqueue.argtypes = [vp]
+    L.ntl_batch_wait.argtypes = [vp]
     L.ntl_batch_download.argtypes = [vp, C.POINTER(vp)]
     L.ntl_get_timings.argtypes = [vp, C.POINTER(Timings)]
     L.ntl_stream.argtypes = [vp]

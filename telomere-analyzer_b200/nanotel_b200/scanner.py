@@ -130,6 +130,12 @@ class Scanner:
     def run(self) -> None:
         self._check(self._L.ntl_batch_run(self._h))
 
+    def enqueue(self) -> None:
+        self._check(self._L.ntl_batch_enqueue(self._h))
+
+    def wait(self) -> None:
+        self._check(self._L.ntl_batch_wait(self._h))
+
     def download(self) -> np.ndarray:
         out = C.c_void_p()
         self._check(self._L.ntl_batch_download(self._h, C.byref(out)))
