@@ -201,6 +201,8 @@ def main():
     bases = int(meta["bases"])
     sc = Scanner(patterns, tvr, 0.6, S, rc=rc, use_filter=use_filter, right_edge=right_edge, device=local_rank,
                  jit=False if args.no_jit else None)
+    if sc.note and rank == 0:
+        print(sc.note, file=sys.stderr)
 
     def barrier():
         torch.cuda.synchronize()

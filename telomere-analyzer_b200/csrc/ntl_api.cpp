@@ -87,7 +87,7 @@ struct ntl_ctx {
     size_t meta_bytes = 0, off_len = 0, off_woff = 0, off_winoff = 0, off_order = 0, off_fmt = 0;
 
     PinnedBuf h_packed, h_meta, h_results, h_cum, h_stages;
-    DevBuf d_packed, d_meta, d_results, d_cum, d_stages, d_pass, d_counter;
+    DevBuf d_packed, d_meta, d_results, d_cum, d_stages, d_pass, d_counter, d_thr;
     ntl_timings tm;
 };
 
@@ -246,6 +246,22 @@ extern "C" int ntl_create(ntl_ctx **out, const ntl_params *p)
     int bps = 0;
     if (e == cudaSuccess) e = ntl_k_scan_occupancy(&bps);
     if (e == cudaSuccess) e = c->d_counter.ensure(64);
+    if (e == cudaSuccess) {
+        /* thr[w] = smallest covered count for which a window of width w is telomeric, i.e. the smallest c with
+         * !((double)c / (double)w < min_density) (NanoTel.R:467, :751-752) -- found with that very division so the
+         * kernels can classify windows with an integer compare.  Widths reach S + S/2 (merged last window). */
+        const int32_t S = c->dev.S;
+        std::vector<uint16_t> thr((size_t)2 * S + 2, 0);
+        for (int32_t w = 1; w <= 2 * S + 1; w++) {
+            int64_t cnt = (int64_t)(p->min_density * (double)w) - 2;
+            if (cnt < 0) cnt = 0;
+            while (cnt <= w && ((double)cnt / (double)w < p->min_density)) cnt++;
+            thr[w] = (uint16_t)(cnt > 65535 ? 65535 : cnt);
+        }
+        e = c->d_thr.ensure(thr.size() * 2);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(c->d_thr.p, thr.data(), thr.size() * 2, cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
         fail(nullptr, NTL_ERR_CUDA, "CUDA initialisation failed: %s", cudaGetErrorString(e));
@@ -301,7 +317,7 @@ extern "C" void ntl_destroy(ntl_ctx *c)
     if (c->jit) ntl_jit_free(c->jit);
     c->h_packed.release(); c->h_meta.release(); c->h_results.release(); c->h_cum.release(); c->h_stages.release();
     c->d_packed.release(); c->d_meta.release(); c->d_results.release(); c->d_cum.release(); c->d_stages.release();
-    c->d_pass.release(); c->d_counter.release();
+    c->d_pass.release(); c->d_counter.release(); c->d_thr.release();
     for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int k = 0; k < NTL_EVENT_RING; k++)
         for (int i = 0; i < 4; i++) if (c->ring[k][i]) cudaEventDestroy(c->ring[k][i]);
@@ -478,6 +494,7 @@ extern "C" int ntl_batch_enqueue(ntl_ctx *c)
     ra.pass = c->dev.use_filter ? (uint8_t *)c->d_pass.p : nullptr;
     for (int t = 0; t < 3; t++) ra.cum[t] = t < T ? (const uint16_t *)c->d_cum.p + (size_t)t * c->total_windows : nullptr;
     ra.results = c->d_results.p;
+    ra.thr = (const uint16_t *)c->d_thr.p;
     ra.stages = c->dev.debug_stages ? c->d_stages.p : nullptr;
     ra.n_reads = n;
 

@@ -79,6 +79,8 @@ typedef struct {
     const uint8_t  *fmt;               /* [n_reads] 0 = 2-bit, 1 = 4-bit                                          */
     uint8_t        *pass;              /* [n_reads] written by K4, read by K3; NULL when the filter is off        */
     const uint16_t *cum[3];
+    const uint16_t *thr;               /* [2 S + 2] smallest covered count that makes a window of that width
+                                          telomeric: !(count / width < min_density), NanoTel.R:751-758         */
     void           *results;           /* ntl_read_result[n_reads]                                                */
     void           *stages;            /* ntl_stage[n_reads][3] or NULL                                           */
     int32_t         n_reads;

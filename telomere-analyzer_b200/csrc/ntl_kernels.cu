@@ -92,7 +92,7 @@ __device__ __forceinline__ u32 hits32(const ReadView &rv, const ntl_dev_pat &pt,
 
 /* Coverage bits of track t (0 exact, 1 one mismatch, 2 one mismatch + TVR) for positions p0 .. p0+31: the union of
  * the trimmed hit intervals of get_density_iranges (NanoTel.R:308-397). */
-__device__ u32 cov_word(const ReadView &rv, int t, int p0, int lane)
+__device__ __noinline__ u32 cov_word(const ReadView &rv, int t, int p0, int lane)
 {
     u32 cov = 0u;
     const int k = t >= 1 ? 1 : 0;
@@ -125,7 +125,7 @@ __device__ u32 cov_word(const ReadView &rv, int t, int p0, int lane)
 }
 
 /* covered positions of track t inside [lo, hi] (1 <= lo, hi <= L), recomputed from the read */
-__device__ int local_count(const ReadView &rv, int t, int lo, int hi, int lane)
+__device__ __noinline__ int local_count(const ReadView &rv, int t, int lo, int hi, int lane)
 {
     int total = 0;
     for (int p0 = lo; p0 <= hi; p0 += 32) {
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) ntl_filter_kernel(const ntl_read_args a)
 struct WinTab {                 /* the window table of one track (analyze_subtelos :737-764), never materialised */
     const uint16_t *cum;
     int n, S, L;
-    double min_density;
+    int thr_reg, thr_last;      /* smallest telomeric count of a regular window / of this read's last window */
 };
 __device__ __forceinline__ int wt_start(const WinTab &w, int k) { return 1 + k * w.S; }
 __device__ __forceinline__ int wt_end(const WinTab &w, int k) { return k == w.n - 1 ? w.L : (k + 1) * w.S; }
@@ -195,41 +195,59 @@ __device__ __forceinline__ double wt_density(const WinTab &w, int k)
 {
     return (double)wt_count(w, k) / (double)(wt_end(w, k) - wt_start(w, k) + 1);      /* :467 */
 }
-__device__ __forceinline__ bool wt_telo(const WinTab &w, int k)
+/* class == CCCTAA (NanoTel.R:751-758), i.e. !(count / width < min_density): the smallest such count per width was
+ * found on the host with the same double division (thr[width]), so the test is an integer compare here. */
+__device__ __forceinline__ bool wt_telo_count(const WinTab &w, int k, int count)
 {
-    return !(wt_density(w, k) < w.min_density);                                         /* :751-758 */
+    return count >= (k == w.n - 1 ? w.thr_last : w.thr_reg);
 }
+__device__ __forceinline__ bool wt_telo(const WinTab &w, int k) { return wt_telo_count(w, k, wt_count(w, k)); }
 
 /* The run/score machine of find_telo_position (NanoTel.R:1003-1025 forward, :1046-1068 backward) over windows
  * i0, i0+dir, ..., i1 (0-based, inclusive).  Returns the window index at which  in_a_row >= R && score >= T  first
  * holds, or -1; *first = first window of the run that is open when the scan stops (-1 if none). */
-__device__ int run_scan(const WinTab &w, int i0, int i1, int dir, double R, double T, int *first, int lane)
+__device__ __noinline__ int run_scan(const WinTab &w, int i0, int i1, int dir, double R, double T, int *first, int lane)
 {
     double score = 0.0;
     int run_first = -1, in_a_row = 0;
     const int total = (i1 - i0) * dir + 1;
-    for (int done = 0; done < total; done += 32) {
-        const int idx = i0 + dir * (done + lane);
-        const bool valid = done + lane < total;
-        double d = 0.0;
-        bool tel = false;
-        if (valid) { d = wt_density(w, idx); tel = !(d < w.min_density); }
-        const u32 mask = __ballot_sync(NTL_FULL, tel);
-        const int nvalid = total - done < 32 ? total - done : 32;
-        int b = 0;
-        while (b < nvalid) {
-            if (!((mask >> b) & 1u)) {
-                score = 0.0; run_first = -1; in_a_row = 0;
-                const u32 rest = mask >> b;
-                if (rest == 0u) break;
-                b += __ffs((int)rest) - 1;
-                continue;
+    /* 128 windows per step: four independent loads per lane are in flight before the first ballot */
+    for (int done = 0; done < total; done += 128) {
+        int cnt[4];
+        u32 mask[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int o = done + 32 * u + lane;
+            cnt[u] = o < total ? wt_count(w, i0 + dir * o) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int o = done + 32 * u + lane;
+            mask[u] = __ballot_sync(NTL_FULL, cnt[u] >= 0 && wt_telo_count(w, i0 + dir * o, cnt[u]));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int base = done + 32 * u;
+            if (base >= total) break;
+            if (mask[u] == 0u) { score = 0.0; run_first = -1; in_a_row = 0; continue; }
+            const int nvalid = total - base < 32 ? total - base : 32;
+            int b = 0;
+            while (b < nvalid) {
+                if (!((mask[u] >> b) & 1u)) {
+                    score = 0.0; run_first = -1; in_a_row = 0;
+                    const u32 rest = mask[u] >> b;
+                    if (rest == 0u) break;
+                    b += __ffs((int)rest) - 1;
+                    continue;
+                }
+                const int idx = i0 + dir * (base + b);
+                const int c = __shfl_sync(NTL_FULL, cnt[u], b);
+                in_a_row += 1;
+                score = score + (double)c / (double)(wt_end(w, idx) - wt_start(w, idx) + 1);   /* :1014 */
+                if (run_first == -1) run_first = idx;
+                if ((double)in_a_row >= R && score >= T) { *first = run_first; return idx; }
+                b += 1;
             }
-            in_a_row += 1;
-            score = score + __shfl_sync(NTL_FULL, d, b);
-            if (run_first == -1) run_first = i0 + dir * (done + b);
-            if ((double)in_a_row >= R && score >= T) { *first = run_first; return i0 + dir * (done + b); }
-            b += 1;
         }
     }
     *first = run_first;
@@ -237,7 +255,7 @@ __device__ int run_scan(const WinTab &w, int i0, int i1, int dir, double R, doub
 }
 
 /* find_telo_position (NanoTel.R:973-1077) */
-__device__ void find_telo_position(const WinTab &w, double R, double T, int *ps, int *pe, int lane)
+__device__ __noinline__ void find_telo_position(const WinTab &w, double R, double T, int *ps, int *pe, int lane)
 {
     const int n = w.n;
     int first = -1;
@@ -260,7 +278,7 @@ __device__ void find_telo_position(const WinTab &w, double R, double T, int *ps,
 }
 
 /* find_left_telo (NanoTel.R:906-959) */
-__device__ void find_left_telo(const WinTab &w, int *ps, int *pe)
+__device__ __noinline__ void find_left_telo(const WinTab &w, int *ps, int *pe)
 {
     int start = 1, end = 1, last_i = 0;
     const int n = w.n;
@@ -278,7 +296,7 @@ __device__ void find_left_telo(const WinTab &w, int *ps, int *pe)
 }
 
 /* find_right_telo (NanoTel.R:843-899); n == 0 is the caller's REF_ERROR case */
-__device__ void find_right_telo(const WinTab &w, int *ps, int *pe)
+__device__ __noinline__ void find_right_telo(const WinTab &w, int *ps, int *pe)
 {
     int start = 1, end = 1, last_i = 0;
     const int n = w.n;
@@ -297,7 +315,7 @@ __device__ void find_right_telo(const WinTab &w, int *ps, int *pe)
 
 /* covered bases of track t inside [a, b] (get_sub_density's numerator, NanoTel.R:467): whole windows come from
  * K2's prefixes, partial windows are recomputed from the read. */
-__device__ int covered_in(const ReadView &rv, const WinTab &w, int t, int a, int b, int lane)
+__device__ __noinline__ int covered_in(const ReadView &rv, const WinTab &w, int t, int a, int b, int lane)
 {
     const int lo = a < 1 ? 1 : a, hi = b > rv.L ? rv.L : b;
     if (hi < lo) return 0;
@@ -320,34 +338,35 @@ __device__ int covered_in(const ReadView &rv, const WinTab &w, int t, int a, int
 
 __device__ __forceinline__ double density_of(const ReadView &rv, const WinTab &w, int t, int a, int b, int lane)
 {
-    return (double)covered_in(rv, w, t, a, b, lane) / (double)(b - a + 1);
+    const int cv = covered_in(rv, w, t, a, b, lane);
+    return cv == 0 ? 0.0 : (double)cv / (double)(b - a + 1);      /* 0 / width is +0.0 exactly */
 }
 
 /* Range starts / ends of `ranges` (raw exact hits of the single fixed pattern, or the reduced runs of the coverage,
  * NanoTel.R:349-354 vs :341-345) inside a span of <= 8 words starting at position sp0. */
 struct SpanBits { u32 st[8]; u32 en[8]; u32 cov[8]; int sp0; int nw; };
 
-__device__ void build_span(const ReadView &rv, int t, int sp0, int nw, SpanBits &sb, int lane)
+__device__ __noinline__ void build_span(const ReadView &rv, int t, int sp0, int nw, SpanBits &sb, int lane)
 {
     sb.sp0 = sp0; sb.nw = nw;
     u32 covw[10];
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 10; i++) covw[i] = 0u;
     /* coverage for words -1 .. nw (one extra word on each side for the run-boundary tests) */
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 10; i++)
         if (i < nw + 2) covw[i] = cov_word(rv, t, sp0 + 32 * (i - 1), lane);
     const bool raw = (t == 0) && c_prm.raw_hits_A;
     u32 hs[10];
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 10; i++) hs[i] = 0u;
     if (raw) {
         const ntl_dev_pat &pt = c_prm.main_pat[0];
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 10; i++)
             if (i < nw + 1) hs[i] = hits32(rv, pt, 0, -1, sp0 + 32 * (i - 1), 1, rv.L, lane);
     }
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 8; i++) {
         if (i < nw) {
             const u32 c = covw[i + 1], cp = covw[i], cn = covw[i + 2];
@@ -365,9 +384,9 @@ __device__ void build_span(const ReadView &rv, int t, int sp0, int nw, SpanBits 
 
 /* smallest / largest position with a set bit inside [lo, hi]; INT_MIN-like -999999999 if none */
 #define NTL_NONE (-999999999)
-__device__ int span_min(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
+__device__ __noinline__ int span_min(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
 {
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 8; i++) {
         if (i >= nw) break;
         const int p0 = sp0 + 32 * i;
@@ -379,9 +398,9 @@ __device__ int span_min(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
     }
     return NTL_NONE;
 }
-__device__ int span_max(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
+__device__ __noinline__ int span_max(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
 {
-#pragma unroll
+#pragma unroll 1
     for (int i = 7; i >= 0; i--) {
         if (i >= nw) continue;
         const int p0 = sp0 + 32 * i;
@@ -393,10 +412,10 @@ __device__ int span_max(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
     }
     return NTL_NONE;
 }
-__device__ int span_popc(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
+__device__ __noinline__ int span_popc(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
 {
     int total = 0;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 8; i++) {
         if (i >= nw) break;
         const int p0 = sp0 + 32 * i;
@@ -409,7 +428,7 @@ __device__ int span_popc(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
 }
 
 /* get_accurate_end (NanoTel.R:1692-1721) */
-__device__ int get_accurate_end(const ReadView &rv, int t, int telo_end, int lane)
+__device__ __noinline__ int get_accurate_end(const ReadView &rv, int t, int telo_end, int lane)
 {
     if (telo_end == -1) return -1;
     SpanBits sb;
@@ -423,7 +442,7 @@ __device__ int get_accurate_end(const ReadView &rv, int t, int telo_end, int lan
 }
 
 /* get_accurate_start (NanoTel.R:1726-1764) */
-__device__ int get_accurate_start(const ReadView &rv, int t, int telo_start, int lane)
+__device__ __noinline__ int get_accurate_start(const ReadView &rv, int t, int telo_start, int lane)
 {
     if (telo_start == -1) return telo_start;
     const int s = telo_start;
@@ -450,7 +469,7 @@ __device__ int get_accurate_start(const ReadView &rv, int t, int telo_start, int
 /* One 18-bp window of search_left/right_patterns (multi_pattern_step_*, NanoTel.R:496-575, :614, :676):
  * matchPattern on subseq(read, a, b) with the default fixed = TRUE, the window's own out-of-bounds rule, hits not
  * trimmed.  Returns false if no pattern hits. */
-__device__ bool step_window(const ReadView &rv, int a, int b, int k, bool use_tvr, int *min_start, int *max_end, int lane)
+__device__ __noinline__ bool step_window(const ReadView &rv, int a, int b, int k, bool use_tvr, int *min_start, int *max_end, int lane)
 {
     bool any = false;
     int mn = 0, mx = 0;
@@ -479,7 +498,7 @@ __device__ bool step_window(const ReadView &rv, int a, int b, int k, bool use_tv
 }
 
 /* search_left_patterns (NanoTel.R:576-633) */
-__device__ int search_left(const ReadView &rv, int start_index, int k, bool use_tvr, int lane)
+__device__ __noinline__ int search_left(const ReadView &rv, int start_index, int k, bool use_tvr, int lane)
 {
     int subseq_start = start_index - 18 > 1 ? start_index - 18 : 1;
     int new_start = start_index;
@@ -496,7 +515,7 @@ __device__ int search_left(const ReadView &rv, int start_index, int k, bool use_
 }
 
 /* search_right_patterns (NanoTel.R:635-697) */
-__device__ int search_right(const ReadView &rv, int end_index, int k, bool use_tvr, int lane)
+__device__ __noinline__ int search_right(const ReadView &rv, int end_index, int k, bool use_tvr, int lane)
 {
     int subseq_end = end_index + 18 < rv.L ? end_index + 18 : rv.L;
     int new_end = end_index;
@@ -538,7 +557,8 @@ __global__ void __launch_bounds__(128) ntl_locate_kernel(const ntl_read_args a)
         for (int t = 0; t < T && !err; t++) {
             WinTab w;
             w.cum = a.cum[t] + a.win_off[r]; w.n = n_win > 0 ? n_win : 0; w.S = S; w.L = rv.L;
-            w.min_density = c_prm.min_density;
+            w.thr_reg = (int)a.thr[S];
+            w.thr_last = w.n > 0 ? (int)a.thr[wt_end(w, w.n - 1) - wt_start(w, w.n - 1) + 1] : 0;
             const int k = t >= 1 ? 1 : 0;
             const bool use_tvr = t == 2;
 

@@ -13,9 +13,9 @@
  *     (1 KiB per warp per step, fully coalesced); the next step's quad is prefetched into registers;
  *   - matching is Shift-And in its position-parallel form: one 32-bit word holds 32 text positions, a pattern
  *     letter is one boolean function of the two bit-planes (LOP3), its j-th letter is aligned with a funnel
- *     shift, and mismatches are counted in a 2-bit bit-sliced saturating counter (ones/twos):
- *         exact hit  = ~(ones | twos)         (track A)
- *         <=1 hit    = ~twos                  (track B)
+ *     shift, and letters are combined three at a time into an (all equal, at most one differs) pair
+ *     (AND3 / MAJ3, one LOP3 each); pairs combine as  EX' = EX & ex,  LE' = (EX & le) | (LE & ex):
+ *         exact hit  = EX   (track A)          <=1-mismatch hit = LE   (track B)
  *     positions outside [1, L] carry an all-zero "equal" mask, which reproduces Biostrings' rule that
  *     out-of-bounds letters are mismatches (hits may start at 0 or end at L+1 with one mismatch, App. B.3);
  *   - coverage (IRanges::union of the hit intervals, then trim) = hit-start mask dilated by the pattern length
@@ -26,8 +26,8 @@
  *     differences.
  *
  * Compiled twice from this one source: by nvcc with the patterns in __constant__ memory (any pattern set), and by
- * NVRTC at ntl_create() with the pattern set baked in (NTL_JIT), which turns every pattern letter into a single
- * LOP3 and fully unrolls the letter loops.
+ * NVRTC at ntl_create() with the pattern set and subseq_length baked in (NTL_JIT), which turns every pattern
+ * letter into a single LOP3, shares equal letters, and fully unrolls the letter and window-end loops.
  */
 #ifndef NTL_SCAN_CUH
 #define NTL_SCAN_CUH
@@ -40,8 +40,6 @@ typedef unsigned int u32;
 /* c_prm (__constant__ ntl_dev_params) is defined by the including .cu file before this header */
 #define PRM_S        (c_prm.S)
 #define PRM_NTRACKS  (c_prm.n_tracks)
-#define PRM_NMAIN    (c_prm.n_main)
-#define PRM_NTVR     (c_prm.n_tvr)
 #define PRM_MAIN_LEN(p) (c_prm.main_pat[p].m)
 #define PRM_TVR_LEN(p)  (c_prm.tvr_pat[p].m)
 #define PRM_NMAIN_GROUPS (c_prm.n_main_groups)
@@ -50,11 +48,10 @@ typedef unsigned int u32;
 #define PRM_TVR_GBEGIN(g)  (c_prm.tvr_group_begin[g])
 #define NTL_UNROLL_PAT _Pragma("unroll 1")
 #define NTL_UNROLL_LET _Pragma("unroll 1")
+#define NTL_UNROLL_WEND _Pragma("unroll 1")
 #else
 #define PRM_S        NTL_J_S
 #define PRM_NTRACKS  NTL_J_NTRACKS
-#define PRM_NMAIN    NTL_J_NMAIN
-#define PRM_NTVR     NTL_J_NTVR
 #define PRM_MAIN_LEN(p) (NTL_J_MAIN_LEN[p])
 #define PRM_TVR_LEN(p)  (NTL_J_TVR_LEN[p])
 #define PRM_NMAIN_GROUPS NTL_J_NMAIN_GROUPS
@@ -63,6 +60,7 @@ typedef unsigned int u32;
 #define PRM_TVR_GBEGIN(g)  (NTL_J_TVR_GBEGIN[g])
 #define NTL_UNROLL_PAT _Pragma("unroll")
 #define NTL_UNROLL_LET _Pragma("unroll")
+#define NTL_UNROLL_WEND _Pragma("unroll")
 #endif
 
 #define NTL_FULL 0xffffffffu
@@ -100,6 +98,14 @@ __device__ __forceinline__ u32 ntl_eq2(u32 hi, u32 lo, u32 v, u32 t0, u32 t1, u3
     return ((hi & b) | (~hi & a)) & v;
 }
 
+/* n <= 3 aligned letter masks -> (all equal, at most one differs) */
+__device__ __forceinline__ void ntl_group3(int n, u32 a, u32 b, u32 c, u32 &ex, u32 &le)
+{
+    if (n == 1) { ex = a; le = NTL_FULL; }
+    else if (n == 2) { ex = a & b; le = a | b; }
+    else { ex = a & b & c; le = (a & b) | (a & c) | (b & c); }
+}
+
 /* Dilate hit starts forward by m positions, in place, over 5 words (word 4 receives the spill of word 3). */
 __device__ __forceinline__ void ntl_dilate5(u32 (&d)[5], int m)
 {
@@ -115,6 +121,63 @@ __device__ __forceinline__ void ntl_dilate5(u32 (&d)[5], int m)
 #pragma unroll
         for (int i = 4; i >= 1; i--) d[i] |= __funnelshift_l(d[i - 1], d[i], s);
         d[0] |= d[0] << s;
+    }
+}
+
+/* aligned "equal" mask of letter j of one pattern for the lane's 4 words: x[i] bit b <=> position (32 i + b + j)
+ * carries a base the letter accepts.  pl: planes [NPL][5], v: validity [5]. */
+template <int NPL, bool TVR>
+__device__ __forceinline__ void ntl_letter(int p, int j, const u32 (&pl)[NPL][5], const u32 (&v)[5], u32 (&x)[4])
+{
+    u32 e[5];
+#ifndef NTL_JIT
+    const ntl_dev_pat &pt = TVR ? c_prm.tvr_pat[p] : c_prm.main_pat[p];
+    if constexpr (NPL == 2) {
+        const u32 t0 = pt.mux2[j][0], t1 = pt.mux2[j][1], t2 = pt.mux2[j][2], t3 = pt.mux2[j][3];
+#pragma unroll
+        for (int i = 0; i < 5; i++) e[i] = ntl_eq2(pl[1][i], pl[0][i], v[i], t0, t1, t2, t3);
+    } else {
+        const u32 nb = pt.nib[j];
+        const u32 mA = (nb & 1u) ? NTL_FULL : 0u, mC = (nb & 2u) ? NTL_FULL : 0u;
+        const u32 mG = (nb & 4u) ? NTL_FULL : 0u, mT = (nb & 8u) ? NTL_FULL : 0u;
+        const bool fx = pt.fixed != 0;
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            u32 any = (pl[0][i] & mA) | (pl[1][i] & mC) | (pl[2][i] & mG) | (pl[3][i] & mT);
+            u32 dif = (pl[0][i] ^ mA) | (pl[1][i] ^ mC) | (pl[2][i] ^ mG) | (pl[3][i] ^ mT);
+            e[i] = (fx ? ~dif : any) & v[i];
+        }
+    }
+#else
+#pragma unroll
+    for (int i = 0; i < 5; i++)
+        e[i] = TVR ? ntl_jit_eq_tvr(p, j, pl[1][i], pl[0][i], v[i]) : ntl_jit_eq_main(p, j, pl[1][i], pl[0][i], v[i]);
+#endif
+#pragma unroll
+    for (int i = 0; i < 4; i++) x[i] = __funnelshift_r(e[i], e[i + 1], j);
+}
+
+/* hit-start masks of one pattern over the lane's 4 words: EX = exact, LE = at most one mismatch */
+template <int NPL, bool TVR>
+__device__ __forceinline__ void ntl_pattern_hits(int p, int m, const u32 (&pl)[NPL][5], const u32 (&v)[5],
+                                                 u32 (&EX)[4], u32 (&LE)[4])
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++) { EX[i] = NTL_FULL; LE[i] = NTL_FULL; }
+    NTL_UNROLL_LET
+    for (int j0 = 0; j0 < m; j0 += 3) {
+        const int n = m - j0 < 3 ? m - j0 : 3;
+        u32 x0[4], x1[4] = {0u, 0u, 0u, 0u}, x2[4] = {0u, 0u, 0u, 0u};
+        ntl_letter<NPL, TVR>(p, j0, pl, v, x0);
+        if (n > 1) ntl_letter<NPL, TVR>(p, j0 + 1, pl, v, x1);
+        if (n > 2) ntl_letter<NPL, TVR>(p, j0 + 2, pl, v, x2);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            u32 ex, le;
+            ntl_group3(n, x0[i], x1[i], x2[i], ex, le);
+            if (!TVR) LE[i] = (EX[i] & le) | (LE[i] & ex);
+            EX[i] &= ex;
+        }
     }
 }
 
@@ -135,6 +198,7 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
     const int n_words = (L >> 5) + 1;
     const int n_quads = (n_words + 3) >> 2;
     const int n_chunks = (n_quads + 31) >> 5;
+    const int last_chunk = L >> 12;                /* chunk holding position L = end of the last window */
     constexpr int QW = NPL * 4;                    /* words per quad */
 
     u32 carry[3] = {0u, 0u, 0u};                   /* coverage spill of the previous chunk's lane 31 -> lane 0 */
@@ -177,8 +241,13 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
         }
         const int pos0 = (c * 32 + lane) * NTL_LANE_BITS;      /* bit index = 1-based position */
         u32 v[5];
+        if (c == 0 || c + 2 >= n_chunks) {                     /* only the read's ends have invalid positions */
 #pragma unroll
-        for (int i = 0; i < 5; i++) v[i] = ntl_valid_word(pos0 + 32 * i, L);
+            for (int i = 0; i < 5; i++) v[i] = ntl_valid_word(pos0 + 32 * i, L);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 5; i++) v[i] = NTL_FULL;
+        }
 
         u32 cov[3][5];
 #pragma unroll
@@ -187,54 +256,21 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
             for (int i = 0; i < 5; i++) cov[t][i] = 0u;
 
         /* ---- main patterns: tracks A and B (get_density_iranges :327-356) */
-        {
+        NTL_UNROLL_PAT
+        for (int g = 0; g < PRM_NMAIN_GROUPS; g++) {
+            const int m = PRM_MAIN_LEN(PRM_MAIN_GBEGIN(g));
+            u32 hA[5] = {0u, 0u, 0u, 0u, 0u}, hB[5] = {0u, 0u, 0u, 0u, 0u};
             NTL_UNROLL_PAT
-            for (int g = 0; g < PRM_NMAIN_GROUPS; g++) {
-                const int m = PRM_MAIN_LEN(PRM_MAIN_GBEGIN(g));
-                u32 hA[5] = {0u, 0u, 0u, 0u, 0u}, hB[5] = {0u, 0u, 0u, 0u, 0u};
-                NTL_UNROLL_PAT
-                for (int p = PRM_MAIN_GBEGIN(g); p < PRM_MAIN_GBEGIN(g + 1); p++) {
-                    u32 ones[4] = {0u, 0u, 0u, 0u}, twos[4] = {0u, 0u, 0u, 0u};
-                    NTL_UNROLL_LET
-                    for (int j = 0; j < m; j++) {
-                        u32 e[5];
-#ifndef NTL_JIT
-                        if constexpr (NPL == 2) {
-                            const u32 t0 = c_prm.main_pat[p].mux2[j][0], t1 = c_prm.main_pat[p].mux2[j][1];
-                            const u32 t2 = c_prm.main_pat[p].mux2[j][2], t3 = c_prm.main_pat[p].mux2[j][3];
+            for (int p = PRM_MAIN_GBEGIN(g); p < PRM_MAIN_GBEGIN(g + 1); p++) {
+                u32 EX[4], LE[4];
+                ntl_pattern_hits<NPL, false>(p, m, pl, v, EX, LE);
 #pragma unroll
-                            for (int i = 0; i < 5; i++) e[i] = ntl_eq2(pl[NPL - 1][i], pl[0][i], v[i], t0, t1, t2, t3);
-                        } else {
-                            const u32 nb = c_prm.main_pat[p].nib[j];
-                            const u32 mA = (nb & 1u) ? NTL_FULL : 0u, mC = (nb & 2u) ? NTL_FULL : 0u;
-                            const u32 mG = (nb & 4u) ? NTL_FULL : 0u, mT = (nb & 8u) ? NTL_FULL : 0u;
-                            const bool fx = c_prm.main_pat[p].fixed != 0;
-#pragma unroll
-                            for (int i = 0; i < 5; i++) {
-                                u32 any = (pl[0][i] & mA) | (pl[1][i] & mC) | (pl[2][i] & mG) | (pl[3][i] & mT);
-                                u32 dif = (pl[0][i] ^ mA) | (pl[1][i] ^ mC) | (pl[2][i] ^ mG) | (pl[3][i] ^ mT);
-                                e[i] = (fx ? ~dif : any) & v[i];
-                            }
-                        }
-#else
-#pragma unroll
-                        for (int i = 0; i < 5; i++) e[i] = ntl_jit_eq_main(p, j, pl[NPL - 1][i], pl[0][i], v[i]);
-#endif
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            u32 x = ~__funnelshift_r(e[i], e[i + 1], j);
-                            twos[i] |= ones[i] & x;
-                            ones[i] ^= x;
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; i++) { hA[i] |= ~(ones[i] | twos[i]); hB[i] |= ~twos[i]; }
-                }
-                ntl_dilate5(hA, m);
-                ntl_dilate5(hB, m);
-#pragma unroll
-                for (int i = 0; i < 5; i++) { cov[0][i] |= hA[i]; cov[1][i] |= hB[i]; }
+                for (int i = 0; i < 4; i++) { hA[i] |= EX[i]; hB[i] |= LE[i]; }
             }
+            ntl_dilate5(hA, m);
+            ntl_dilate5(hB, m);
+#pragma unroll
+            for (int i = 0; i < 5; i++) { cov[0][i] |= hA[i]; cov[1][i] |= hB[i]; }
         }
         /* ---- TVR patterns, exact: track C = B + TVR (get_density_iranges :360-393) */
         if (T == 3) {
@@ -244,37 +280,10 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
                 u32 hC[5] = {0u, 0u, 0u, 0u, 0u};
                 NTL_UNROLL_PAT
                 for (int p = PRM_TVR_GBEGIN(g); p < PRM_TVR_GBEGIN(g + 1); p++) {
-                    u32 mis[4] = {0u, 0u, 0u, 0u};
-                    NTL_UNROLL_LET
-                    for (int j = 0; j < m; j++) {
-                        u32 e[5];
-#ifndef NTL_JIT
-                        if constexpr (NPL == 2) {
-                            const u32 t0 = c_prm.tvr_pat[p].mux2[j][0], t1 = c_prm.tvr_pat[p].mux2[j][1];
-                            const u32 t2 = c_prm.tvr_pat[p].mux2[j][2], t3 = c_prm.tvr_pat[p].mux2[j][3];
+                    u32 EX[4], LE[4];
+                    ntl_pattern_hits<NPL, true>(p, m, pl, v, EX, LE);
 #pragma unroll
-                            for (int i = 0; i < 5; i++) e[i] = ntl_eq2(pl[NPL - 1][i], pl[0][i], v[i], t0, t1, t2, t3);
-                        } else {
-                            const u32 nb = c_prm.tvr_pat[p].nib[j];
-                            const u32 mA = (nb & 1u) ? NTL_FULL : 0u, mC = (nb & 2u) ? NTL_FULL : 0u;
-                            const u32 mG = (nb & 4u) ? NTL_FULL : 0u, mT = (nb & 8u) ? NTL_FULL : 0u;
-                            const bool fx = c_prm.tvr_pat[p].fixed != 0;
-#pragma unroll
-                            for (int i = 0; i < 5; i++) {
-                                u32 any = (pl[0][i] & mA) | (pl[1][i] & mC) | (pl[2][i] & mG) | (pl[3][i] & mT);
-                                u32 dif = (pl[0][i] ^ mA) | (pl[1][i] ^ mC) | (pl[2][i] ^ mG) | (pl[3][i] ^ mT);
-                                e[i] = (fx ? ~dif : any) & v[i];
-                            }
-                        }
-#else
-#pragma unroll
-                        for (int i = 0; i < 5; i++) e[i] = ntl_jit_eq_tvr(p, j, pl[NPL - 1][i], pl[0][i], v[i]);
-#endif
-#pragma unroll
-                        for (int i = 0; i < 4; i++) mis[i] |= ~__funnelshift_r(e[i], e[i + 1], j);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; i++) hC[i] |= ~mis[i];
+                    for (int i = 0; i < 4; i++) hC[i] |= EX[i];
                 }
                 ntl_dilate5(hC, m);
 #pragma unroll
@@ -288,22 +297,20 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
         u32 pc[3][4], tot[3];
 #pragma unroll
         for (int t = 0; t < 3; t++) {
+            tot[t] = 0u;
+#pragma unroll
+            for (int i = 0; i < 4; i++) pc[t][i] = 0u;
             if (t < T) {
                 u32 sp = __shfl_up_sync(NTL_FULL, cov[t][4], 1);
                 if (lane == 0) sp = carry[t];
                 carry[t] = __shfl_sync(NTL_FULL, cov[t][4], 31);
                 cov[t][0] |= sp;
-                tot[t] = 0u;
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     cov[t][i] &= v[i];
                     pc[t][i] = (u32)__popc(cov[t][i]);
                     tot[t] += pc[t][i];
                 }
-            } else {
-                tot[t] = 0u;
-#pragma unroll
-                for (int i = 0; i < 4; i++) pc[t][i] = 0u;
             }
         }
         /* ---- packed warp scan: (A | B << 16) and C; each lane total <= 128, chunk total <= 4096 */
@@ -311,36 +318,49 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             u32 y01 = __shfl_up_sync(NTL_FULL, s01, d);
-            u32 y2 = __shfl_up_sync(NTL_FULL, s2, d);
-            if (lane >= d) { s01 += y01; s2 += y2; }
+            if (lane >= d) s01 += y01;
+            if (T == 3) {
+                u32 y2 = __shfl_up_sync(NTL_FULL, s2, d);
+                if (lane >= d) s2 += y2;
+            }
         }
         u32 ex[3];
         ex[0] = run[0] + (s01 & 0xffffu) - tot[0];
         ex[1] = run[1] + (s01 >> 16) - tot[1];
         ex[2] = run[2] + s2 - tot[2];
         {
-            u32 l01 = __shfl_sync(NTL_FULL, s01, 31), l2 = __shfl_sync(NTL_FULL, s2, 31);
-            run[0] += l01 & 0xffffu; run[1] += l01 >> 16; run[2] += l2;
+            u32 l01 = __shfl_sync(NTL_FULL, s01, 31);
+            run[0] += l01 & 0xffffu; run[1] += l01 >> 16;
+            if (T == 3) run[2] += __shfl_sync(NTL_FULL, s2, 31);
         }
+        /* bytes 1..3 of pre[t] = covered bases of this lane before word 1..3 (each <= 96) */
+        u32 pre[3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) pre[t] = pc[t][0] * 0x01010100u + pc[t][1] * 0x01010000u + pc[t][2] * 0x01000000u;
 
-        /* ---- window ends inside this lane's 128 positions: regular ends at multiples of S (index kq-1, only
-         *      kq <= n_win-1), and the last window's end at L (index n_win-1; split_telo :218, :223) */
-        {
-            int o = off, k = kq;
-            const int rel_last = L - pos0;
-            bool do_last = rel_last >= 0 && rel_last < NTL_LANE_BITS;
-            while (o < NTL_LANE_BITS || do_last) {
-                int rel, idx;
-                if (o < NTL_LANE_BITS) { rel = o; idx = k - 1; o += S; k += 1; if (idx < 0 || idx > n_win - 2) continue; }
-                else { rel = rel_last; idx = n_win - 1; do_last = false; }
+        /* ---- window ends inside this lane's 128 positions.  Regular ends are the multiples of S with index
+         *      kq-1 <= n_win-2; the last window ends at L (index n_win-1; split_telo :218, :223). */
+        const int n_ends = (NTL_LANE_BITS - 1) / S + 1;        /* most multiples of S inside 128 positions */
+        NTL_UNROLL_WEND
+        for (int it = 0; it <= n_ends; it++) {
+            int rel, idx;
+            bool act;
+            if (it < n_ends) {
+                rel = off + it * S; idx = kq + it - 1;
+                act = rel < NTL_LANE_BITS && idx >= 0 && idx <= n_win - 2;
+            } else {
+                if (c != last_chunk) break;                    /* warp-uniform */
+                rel = L - pos0; idx = n_win - 1;
+                act = rel >= 0 && rel < NTL_LANE_BITS;
+            }
+            if (act) {
                 const int wi = rel >> 5;
                 const u32 bm = NTL_FULL >> (31 - (rel & 31));
 #pragma unroll
                 for (int t = 0; t < 3; t++) {
                     if (t < T) {
-                        u32 wv = wi == 0 ? cov[t][0] : wi == 1 ? cov[t][1] : wi == 2 ? cov[t][2] : cov[t][3];
-                        u32 bf = wi == 0 ? 0u : wi == 1 ? pc[t][0] : wi == 2 ? pc[t][0] + pc[t][1]
-                                                                            : pc[t][0] + pc[t][1] + pc[t][2];
+                        const u32 wv = wi == 0 ? cov[t][0] : wi == 1 ? cov[t][1] : wi == 2 ? cov[t][2] : cov[t][3];
+                        const u32 bf = (pre[t] >> (8 * wi)) & 0xffu;
                         a.cum[t][wo + idx] = (uint16_t)(ex[t] + bf + (u32)__popc(wv & bm));
                     }
                 }
