@@ -113,7 +113,7 @@ typedef struct {        /* wall/device times of the last batch, milliseconds */
     int32_t kernel_launches;/* kernels launched by the passes the last ntl_batch_wait covered                */
     int32_t scan_is_jit;    /* 1 if the NVRTC-specialised scan kernel ran                                    */
     int32_t steps;          /* passes covered by filter_ms / scan_ms / locate_ms (sums over those passes)    */
-    int32_t reserved;
+    int32_t candidates;     /* reads of the last pass that needed the full locate kernel (the rest ended in triage) */
 } ntl_timings;
 
 typedef struct ntl_ctx ntl_ctx;

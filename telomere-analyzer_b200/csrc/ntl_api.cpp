@@ -27,7 +27,9 @@ cudaError_t ntl_k_set_params(const ntl_dev_params *p, cudaStream_t st);
 cudaError_t ntl_k_scan(const ntl_scan_args *a, int four_bit, int grid, cudaStream_t st);
 cudaError_t ntl_k_scan_occupancy(int *blocks_per_sm);
 cudaError_t ntl_k_filter(const ntl_read_args *a, cudaStream_t st);
-cudaError_t ntl_k_locate(const ntl_read_args *a, cudaStream_t st);
+cudaError_t ntl_k_triage(const ntl_read_args *a, cudaStream_t st);
+cudaError_t ntl_k_locate(const ntl_read_args *a, int grid, cudaStream_t st);
+cudaError_t ntl_k_locate_occupancy(int *blocks_per_sm);
 }
 
 namespace {
@@ -73,7 +75,7 @@ struct ntl_ctx {
     ntl_params prm;
     std::vector<std::string> pat_store, tvr_store;
     ntl_dev_params dev;
-    int device = 0, n_sms = 0, scan_grid = 0, host_threads = 1;
+    int device = 0, n_sms = 0, scan_grid = 0, locate_grid = 0, host_threads = 1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr};
     cudaEvent_t ring[NTL_EVENT_RING][4] = {{nullptr}};
@@ -87,7 +89,7 @@ struct ntl_ctx {
     size_t meta_bytes = 0, off_len = 0, off_woff = 0, off_winoff = 0, off_order = 0, off_fmt = 0;
 
     PinnedBuf h_packed, h_meta, h_results, h_cum, h_stages;
-    DevBuf d_packed, d_meta, d_results, d_cum, d_stages, d_pass, d_counter, d_thr;
+    DevBuf d_packed, d_meta, d_results, d_cum, d_stages, d_pass, d_counter, d_thr, d_flags;
     ntl_timings tm;
 };
 
@@ -201,6 +203,12 @@ int digest_params(ntl_ctx *c, const ntl_params *p)
     d.debug_stages = (p->options & NTL_OPT_DEBUG_STAGES) ? 1 : 0;
     d.min_density = p->min_density;
     d.filter_threshold = p->min_density * 0.8;                 /* NanoTel.R:2143 global_min_density*0.8 */
+    {   /* smallest count c with !(c / S < min_density): a width-S window is telomeric from there on (:751-752) */
+        int64_t cnt = (int64_t)(p->min_density * (double)d.S) - 2;
+        if (cnt < 0) cnt = 0;
+        while (cnt <= d.S && ((double)cnt / (double)d.S < p->min_density)) cnt++;
+        d.thr_reg = (int32_t)cnt;
+    }
     return NTL_OK;
 }
 
@@ -271,6 +279,7 @@ extern "C" int ntl_create(ntl_ctx **out, const ntl_params *p)
     c->n_sms = prop.multiProcessorCount;
     if (bps < 1) bps = 1;
     c->scan_grid = c->n_sms * bps;                             /* persistent grid: every CTA resident, 148 x occupancy */
+    { int lb = 0; if (ntl_k_locate_occupancy(&lb) != cudaSuccess || lb < 1) lb = 4; c->locate_grid = c->n_sms * lb; }
 
     /* ---- NVRTC specialisation of the scan kernel for this pattern set */
     if (!(p->options & NTL_OPT_NO_JIT)) {
@@ -317,7 +326,7 @@ extern "C" void ntl_destroy(ntl_ctx *c)
     if (c->jit) ntl_jit_free(c->jit);
     c->h_packed.release(); c->h_meta.release(); c->h_results.release(); c->h_cum.release(); c->h_stages.release();
     c->d_packed.release(); c->d_meta.release(); c->d_results.release(); c->d_cum.release(); c->d_stages.release();
-    c->d_pass.release(); c->d_counter.release(); c->d_thr.release();
+    c->d_pass.release(); c->d_counter.release(); c->d_thr.release(); c->d_flags.release();
     for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int k = 0; k < NTL_EVENT_RING; k++)
         for (int i = 0; i < 4; i++) if (c->ring[k][i]) cudaEventDestroy(c->ring[k][i]);
@@ -365,7 +374,7 @@ extern "C" int ntl_batch_pack(ntl_ctx *c, const char *const *seq, const int64_t 
         h_fmt[i] = 0;
         const int64_t n_words = (L >> 5) + 1;
         words += ((n_words + 3) >> 2) * 8;
-        wins += count_windows(L, S);
+        wins += ((int64_t)count_windows(L, S) + 7) & ~(int64_t)7;   /* each read starts on a 16-byte boundary of the uint16 planes */
         bases += L;
     }
     const int64_t main_words = words;
@@ -452,6 +461,7 @@ extern "C" int ntl_batch_upload(ntl_ctx *c)
     CK(c, c->d_results.ensure((size_t)n * sizeof(ntl_read_result) + 64));
     CK(c, c->d_cum.ensure((size_t)c->total_windows * 2 * T + 64));
     CK(c, c->d_pass.ensure((size_t)n + 64));
+    CK(c, c->d_flags.ensure((size_t)n * 4 + 64));         /* candidate list of the locate kernel */
     if (c->dev.debug_stages) CK(c, c->d_stages.ensure((size_t)n * 3 * sizeof(ntl_stage) + 64));
     CK(c, cudaEventRecord(c->ev[0], c->stream));
     if (c->total_words > 0)
@@ -495,6 +505,9 @@ extern "C" int ntl_batch_enqueue(ntl_ctx *c)
     for (int t = 0; t < 3; t++) ra.cum[t] = t < T ? (const uint16_t *)c->d_cum.p + (size_t)t * c->total_windows : nullptr;
     ra.results = c->d_results.p;
     ra.thr = (const uint16_t *)c->d_thr.p;
+    ra.order = (const int32_t *)(dm + c->off_order);
+    ra.cand = (int32_t *)c->d_flags.p;
+    ra.counters = (uint32_t *)c->d_counter.p + 4;
     ra.stages = c->dev.debug_stages ? c->d_stages.p : nullptr;
     ra.n_reads = n;
 
@@ -531,7 +544,10 @@ extern "C" int ntl_batch_enqueue(ntl_ctx *c)
         launches++;
     }
     CK(c, cudaEventRecord(ev[2], c->stream));
-    if (n > 0) { CK(c, ntl_k_locate(&ra, c->stream)); launches++; }
+    if (n > 0) {
+        CK(c, ntl_k_triage(&ra, c->stream)); launches++;
+        CK(c, ntl_k_locate(&ra, c->locate_grid, c->stream)); launches++;
+    }
     CK(c, cudaEventRecord(ev[3], c->stream));
     c->pending_launches += launches;
     c->pending++;
@@ -556,6 +572,7 @@ extern "C" int ntl_batch_wait(ntl_ctx *c)
         c->tm.filter_ms = f; c->tm.scan_ms = s; c->tm.locate_ms = l;
         c->tm.steps = c->pending;
         c->tm.kernel_launches = c->pending_launches;
+        { uint32_t nc = 0; CK(c, cudaMemcpy(&nc, (uint32_t *)c->d_counter.p + 4, 4, cudaMemcpyDeviceToHost)); c->tm.candidates = (int32_t)nc; }
         c->state = ST_RAN;
     }
     c->pending = 0; c->pending_launches = 0;

@@ -49,6 +49,8 @@ typedef struct {
     int32_t debug_stages;
     int32_t n_main_groups;             /* runs of equal pattern length among main_pat[]                           */
     int32_t n_tvr_groups;
+    int32_t thr_reg;                   /* smallest covered count that makes a width-S window telomeric            */
+    int32_t pad0;
     int32_t main_group_begin[NTL_DEV_MAX_PAT + 1];
     int32_t tvr_group_begin[NTL_DEV_MAX_PAT + 1];
     double  min_density;
@@ -81,6 +83,9 @@ typedef struct {
     const uint16_t *cum[3];
     const uint16_t *thr;               /* [2 S + 2] smallest covered count that makes a window of that width
                                           telomeric: !(count / width < min_density), NanoTel.R:751-758         */
+    const int32_t  *order;             /* [n_reads] read indices, longest first (triage walks reads in this order)   */
+    int32_t        *cand;              /* [n_reads] reads the triage kernel hands on to the locate kernel            */
+    uint32_t       *counters;          /* [0] number of entries in cand[], [1] locate work counter; zeroed per pass   */
     void           *results;           /* ntl_read_result[n_reads]                                                */
     void           *stages;            /* ntl_stage[n_reads][3] or NULL                                           */
     int32_t         n_reads;

@@ -5,10 +5,12 @@
  *   K3  ntl_locate_kernel      per-read locator and refinement     (find_telo_position_wraper NanoTel.R:1080-1155 and
  *                              everything it calls, analyze_read's densities and keep rule :1840-1868)
  *
- * K3/K4 are one warp per read with warp-uniform control flow; lanes evaluate 32 alignments / 32 windows at a time.
- * They re-derive hits locally from the packed read where the reference consults its range list, so that K2 never
- * has to spill per-base masks to HBM.  All fp64 expressions are written exactly as NanoTel.R evaluates them
- * (int/int divisions in double, sums in window order); this file must be compiled with --fmad=false.
+ * K3/K4 are one warp per read with warp-uniform control flow.  Where the reference consults its range list
+ * (get_accurate_start/end, get_sub_density on arbitrary intervals) K3 re-derives hits and coverage locally from
+ * the packed read -- one word (32 positions) per lane, the same bit-parallel matching as K2 -- so that K2 never has
+ * to spill per-base masks to HBM.  Reads whose tracks have no telomeric window at all (K2 leaves a flag) skip the
+ * window table entirely.  All fp64 expressions are written exactly as NanoTel.R evaluates them (int/int divisions
+ * in double, sums in window order); this file must be compiled with --fmad=false.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -31,6 +33,10 @@ __global__ void __launch_bounds__(256) ntl_scan_kernel(const ntl_scan_args a)
 /* =============================================================================================================
  * Shared by K3 and K4: random access into a packed read
  * ============================================================================================================= */
+#define NTL_NONE (-999999999)
+#define NTL_TRIAGE_MAX_WIN 384
+#define NTL_IMAX 2147483647
+
 struct ReadView {
     const u32 *base;
     int L;
@@ -79,8 +85,9 @@ __device__ __forceinline__ int pat_mismatches(const ntl_dev_pat &pt, bool fixed,
     return __popc(~eq & mm);
 }
 
-/* Hit-start bits for alignment starts p0 .. p0+31 of one pattern (Biostrings::matchPattern, App. B.2/B.3):
- * positions outside [vlo, vhi] are mismatches.  mode_fixed < 0: use the pattern's own fixed flag. */
+/* Hit-start bits for alignment starts p0 .. p0+31 of one pattern, one alignment per lane
+ * (Biostrings::matchPattern, App. B.2/B.3): positions outside [vlo, vhi] are mismatches.
+ * mode_fixed < 0: use the pattern's own fixed flag. */
 __device__ __forceinline__ u32 hits32(const ReadView &rv, const ntl_dev_pat &pt, int k, int mode_fixed, int p0, int vlo,
                                       int vhi, int lane)
 {
@@ -90,49 +97,122 @@ __device__ __forceinline__ u32 hits32(const ReadView &rv, const ntl_dev_pat &pt,
     return __ballot_sync(NTL_FULL, pat_mismatches(pt, fx, pl) <= k);
 }
 
-/* Coverage bits of track t (0 exact, 1 one mismatch, 2 one mismatch + TVR) for positions p0 .. p0+31: the union of
- * the trimmed hit intervals of get_density_iranges (NanoTel.R:308-397). */
-__device__ __noinline__ u32 cov_word(const ReadView &rv, int t, int p0, int lane)
+/* ---- one word per lane: planes of read word w as A/C/G/T bit masks, zero outside [1, L] */
+__device__ __forceinline__ void word_planes(const ReadView &rv, int w, u32 (&pl)[4])
 {
-    u32 cov = 0u;
-    const int k = t >= 1 ? 1 : 0;
-    for (int p = 0; p < c_prm.n_main; p++) {
-        const ntl_dev_pat &pt = c_prm.main_pat[p];
-        const u32 h0 = hits32(rv, pt, k, -1, p0 - 32, 1, rv.L, lane);
-        const u32 h1 = hits32(rv, pt, k, -1, p0, 1, rv.L, lane);
-        const unsigned long long H = ((unsigned long long)h1 << 32) | h0;
-        unsigned long long D = H;
-        for (int j = 1; j < pt.m; j++) D |= H << j;
-        cov |= (u32)(D >> 32);
+    if (w < 0 || w >= rv.n_words) { pl[0] = pl[1] = pl[2] = pl[3] = 0u; return; }
+    const u32 vm = ntl_valid_word(w << 5, rv.L);
+    const int q = w >> 2, i = w & 3;
+    if (rv.fmt == 0) {
+        const u32 lo = rv.base[(size_t)q * 8 + i], hi = rv.base[(size_t)q * 8 + 4 + i];
+        pl[0] = ~hi & ~lo & vm; pl[1] = ~hi & lo & vm; pl[2] = hi & lo & vm; pl[3] = hi & ~lo & vm;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) pl[k] = rv.base[(size_t)q * 16 + k * 4 + i] & vm;
     }
-    if (t == 2) {
-        for (int p = 0; p < c_prm.n_tvr; p++) {
-            const ntl_dev_pat &pt = c_prm.tvr_pat[p];
-            const u32 h0 = hits32(rv, pt, 0, -1, p0 - 32, 1, rv.L, lane);
-            const u32 h1 = hits32(rv, pt, 0, -1, p0, 1, rv.L, lane);
-            const unsigned long long H = ((unsigned long long)h1 << 32) | h0;
-            unsigned long long D = H;
-            for (int j = 1; j < pt.m; j++) D |= H << j;
-            cov |= (u32)(D >> 32);
-        }
-    }
-    /* trim() to [1, L] */
-    int lowb = 1 - p0; if (lowb < 0) lowb = 0;
-    int highb = rv.L - p0; if (highb > 31) highb = 31;
-    u32 vm = 0u;
-    if (highb >= lowb) vm = (NTL_FULL >> (31 - highb)) & (NTL_FULL << lowb);
-    return cov & vm;
 }
 
-/* covered positions of track t inside [lo, hi] (1 <= lo, hi <= L), recomputed from the read */
+/* exact / <=1-mismatch hit starts of one pattern inside the lane's word (letters may run into the next word) */
+__device__ __forceinline__ void word_hits(const ntl_dev_pat &pt, const u32 (&pw)[4], const u32 (&pn)[4], u32 *exact,
+                                          u32 *le1)
+{
+    u32 ones = 0u, twos = 0u;
+    const bool fx = pt.fixed != 0;
+#pragma unroll 1
+    for (int j = 0; j < pt.m; j++) {
+        const u32 nb = pt.nib[j];
+        const u32 mA = (nb & 1u) ? NTL_FULL : 0u, mC = (nb & 2u) ? NTL_FULL : 0u;
+        const u32 mG = (nb & 4u) ? NTL_FULL : 0u, mT = (nb & 8u) ? NTL_FULL : 0u;
+        u32 ew, en;
+        if (fx) {
+            ew = ~((pw[0] ^ mA) | (pw[1] ^ mC) | (pw[2] ^ mG) | (pw[3] ^ mT));
+            en = ~((pn[0] ^ mA) | (pn[1] ^ mC) | (pn[2] ^ mG) | (pn[3] ^ mT));
+        } else {
+            ew = (pw[0] & mA) | (pw[1] & mC) | (pw[2] & mG) | (pw[3] & mT);
+            en = (pn[0] & mA) | (pn[1] & mC) | (pn[2] & mG) | (pn[3] & mT);
+        }
+        const u32 x = ~__funnelshift_r(ew, en, j);
+        twos |= ones & x;
+        ones ^= x;
+    }
+    *exact = ~(ones | twos);
+    *le1 = ~twos;
+}
+
+/* Coverage of track t (0 exact, 1 one mismatch, 2 one mismatch + TVR; the union of the trimmed hit intervals of
+ * get_density_iranges, NanoTel.R:308-397) for read words wbase .. wbase+31, one word per lane: lane l holds positions
+ * 32 (wbase + l) .. +31.  Lane 0 lacks the spill of word wbase-1: callers start one word early and ignore lane 0.
+ * *hs = exact hit starts of main pattern 0 (the raw hit list of NanoTel.R:349-354). */
+__device__ __noinline__ u32 warp_cov(const ReadView &rv, int t, int wbase, int lane, u32 *hs)
+{
+    const int w = wbase + lane;
+    u32 pw[4], pn[4];
+    word_planes(rv, w, pw);
+    word_planes(rv, w + 1, pn);
+    u32 cov = 0u, h0 = 0u;
+#pragma unroll 1
+    for (int p = 0; p < c_prm.n_main; p++) {
+        u32 ex, le;
+        word_hits(c_prm.main_pat[p], pw, pn, &ex, &le);
+        if (p == 0) h0 = ex;
+        const u32 H = t >= 1 ? le : ex;
+        u32 Hp = __shfl_up_sync(NTL_FULL, H, 1);
+        if (lane == 0) Hp = 0u;
+#pragma unroll 1
+        for (int j = 0; j < c_prm.main_pat[p].m; j++) cov |= __funnelshift_l(Hp, H, j);
+    }
+    if (t == 2) {
+#pragma unroll 1
+        for (int p = 0; p < c_prm.n_tvr; p++) {
+            u32 ex, le;
+            word_hits(c_prm.tvr_pat[p], pw, pn, &ex, &le);
+            u32 Hp = __shfl_up_sync(NTL_FULL, ex, 1);
+            if (lane == 0) Hp = 0u;
+#pragma unroll 1
+            for (int j = 0; j < c_prm.tvr_pat[p].m; j++) cov |= __funnelshift_l(Hp, ex, j);
+        }
+    }
+    *hs = h0;
+    if (w < 0 || w >= rv.n_words) return 0u;
+    return cov & ntl_valid_word(w << 5, rv.L);          /* trim() to [1, L] */
+}
+
+/* bits of this lane's word that lie inside [lo, hi]; lane 0 is never used (see warp_cov) */
+__device__ __forceinline__ u32 lane_mask(int wbase, int lane, int lo, int hi)
+{
+    const int p0 = (wbase + lane) << 5;
+    int lb = lo - p0; if (lb < 0) lb = 0;
+    int hb = hi - p0; if (hb > 31) hb = 31;
+    if (hb < lb || lane == 0) return 0u;
+    return (NTL_FULL >> (31 - hb)) & (NTL_FULL << lb);
+}
+__device__ __forceinline__ int lanes_min(u32 bits, int wbase, int lane, int lo, int hi)
+{
+    const u32 m = bits & lane_mask(wbase, lane, lo, hi);
+    const int cand = m ? ((wbase + lane) << 5) + __ffs((int)m) - 1 : NTL_IMAX;
+    const int r = __reduce_min_sync(NTL_FULL, cand);
+    return r == NTL_IMAX ? NTL_NONE : r;
+}
+__device__ __forceinline__ int lanes_max(u32 bits, int wbase, int lane, int lo, int hi)
+{
+    const u32 m = bits & lane_mask(wbase, lane, lo, hi);
+    const int cand = m ? ((wbase + lane) << 5) + 31 - __clz((int)m) : -NTL_IMAX;
+    const int r = __reduce_max_sync(NTL_FULL, cand);
+    return r == -NTL_IMAX ? NTL_NONE : r;
+}
+__device__ __forceinline__ int lanes_popc(u32 bits, int wbase, int lane, int lo, int hi)
+{
+    return (int)__reduce_add_sync(NTL_FULL, (unsigned)__popc(bits & lane_mask(wbase, lane, lo, hi)));
+}
+
+/* covered positions of track t inside [lo, hi] (1 <= lo <= hi <= L), recomputed from the read, 992 per step */
 __device__ __noinline__ int local_count(const ReadView &rv, int t, int lo, int hi, int lane)
 {
     int total = 0;
-    for (int p0 = lo; p0 <= hi; p0 += 32) {
-        u32 w = cov_word(rv, t, p0, lane);
-        const int rem = hi - p0;
-        if (rem < 31) w &= NTL_FULL >> (31 - rem);
-        total += __popc(w);
+    for (int wb = (lo >> 5) - 1; ((wb + 1) << 5) <= hi; wb += 31) {
+        u32 hs;
+        const u32 cov = warp_cov(rv, t, wb, lane, &hs);
+        total += lanes_popc(cov, wb, lane, lo, hi);
     }
     return total;
 }
@@ -183,6 +263,7 @@ struct WinTab {                 /* the window table of one track (analyze_subtel
     const uint16_t *cum;
     int n, S, L;
     int thr_reg, thr_last;      /* smallest telomeric count of a regular window / of this read's last window */
+    bool any;                   /* K2 saw at least one telomeric window on this track                         */
 };
 __device__ __forceinline__ int wt_start(const WinTab &w, int k) { return 1 + k * w.S; }
 __device__ __forceinline__ int wt_end(const WinTab &w, int k) { return k == w.n - 1 ? w.L : (k + 1) * w.S; }
@@ -191,17 +272,13 @@ __device__ __forceinline__ int wt_count(const WinTab &w, int k)
     const u32 hi = w.cum[k], lo = k > 0 ? (u32)w.cum[k - 1] : 0u;
     return (int)((hi - lo) & 0xffffu);
 }
-__device__ __forceinline__ double wt_density(const WinTab &w, int k)
-{
-    return (double)wt_count(w, k) / (double)(wt_end(w, k) - wt_start(w, k) + 1);      /* :467 */
-}
 /* class == CCCTAA (NanoTel.R:751-758), i.e. !(count / width < min_density): the smallest such count per width was
- * found on the host with the same double division (thr[width]), so the test is an integer compare here. */
+ * found on the host with the same double division, so the test is an integer compare here. */
 __device__ __forceinline__ bool wt_telo_count(const WinTab &w, int k, int count)
 {
     return count >= (k == w.n - 1 ? w.thr_last : w.thr_reg);
 }
-__device__ __forceinline__ bool wt_telo(const WinTab &w, int k) { return wt_telo_count(w, k, wt_count(w, k)); }
+__device__ __forceinline__ bool wt_telo(const WinTab &w, int k) { return w.any && wt_telo_count(w, k, wt_count(w, k)); }
 
 /* The run/score machine of find_telo_position (NanoTel.R:1003-1025 forward, :1046-1068 backward) over windows
  * i0, i0+dir, ..., i1 (0-based, inclusive).  Returns the window index at which  in_a_row >= R && score >= T  first
@@ -259,7 +336,7 @@ __device__ __noinline__ void find_telo_position(const WinTab &w, double R, doubl
 {
     const int n = w.n;
     int first = -1;
-    int hit = n > 0 ? run_scan(w, 0, n - 1, +1, R, T, &first, lane) : -1;
+    int hit = (n > 0 && w.any) ? run_scan(w, 0, n - 1, +1, R, T, &first, lane) : -1;
     if (hit < 0) { *ps = -1; *pe = -1; return; }                         /* :1026-1028 */
     const int start = wt_start(w, first);
     const int end_position = hit + 2;                                    /* 1-based i + 1 (:1022) */
@@ -282,6 +359,11 @@ __device__ __noinline__ void find_left_telo(const WinTab &w, int *ps, int *pe)
 {
     int start = 1, end = 1, last_i = 0;
     const int n = w.n;
+    if (!w.any) {                       /* no telomeric window anywhere: only the max_diff = 200 test can fire */
+        const bool far = n > 0 && wt_start(w, n - 1) > 200;
+        *ps = far ? -1 : 1; *pe = far ? -1 : 1;
+        return;
+    }
     for (int i = 0; i < n; i++) {
         if (wt_start(w, i) > 200) { *ps = -1; *pe = -1; return; }
         if (!wt_telo(w, i)) continue;
@@ -300,6 +382,11 @@ __device__ __noinline__ void find_right_telo(const WinTab &w, int *ps, int *pe)
 {
     int start = 1, end = 1, last_i = 0;
     const int n = w.n;
+    if (!w.any) {
+        const bool far = n > 0 && wt_end(w, 0) < w.L - 200;
+        *ps = far ? -1 : 1; *pe = far ? -1 : 1;
+        return;
+    }
     for (int i = n - 1; i >= 0; i--) {
         if (wt_end(w, i) < w.L - 200) { *ps = -1; *pe = -1; return; }
         if (!wt_telo(w, i)) continue;
@@ -331,9 +418,7 @@ __device__ __noinline__ int covered_in(const ReadView &rv, const WinTab &w, int 
     if (hi != wt_end(w, khi)) { total += local_count(rv, t, wt_start(w, khi), hi, lane); kl = khi - 1; }
     int part = 0;
     for (int k = kf + lane; k <= kl; k += 32) part += wt_count(w, k);
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(NTL_FULL, part, d);
-    return total + part;
+    return total + (int)__reduce_add_sync(NTL_FULL, (unsigned)part);
 }
 
 __device__ __forceinline__ double density_of(const ReadView &rv, const WinTab &w, int t, int a, int b, int lane)
@@ -342,101 +427,26 @@ __device__ __forceinline__ double density_of(const ReadView &rv, const WinTab &w
     return cv == 0 ? 0.0 : (double)cv / (double)(b - a + 1);      /* 0 / width is +0.0 exactly */
 }
 
-/* Range starts / ends of `ranges` (raw exact hits of the single fixed pattern, or the reduced runs of the coverage,
- * NanoTel.R:349-354 vs :341-345) inside a span of <= 8 words starting at position sp0. */
-struct SpanBits { u32 st[8]; u32 en[8]; u32 cov[8]; int sp0; int nw; };
-
-__device__ __noinline__ void build_span(const ReadView &rv, int t, int sp0, int nw, SpanBits &sb, int lane)
-{
-    sb.sp0 = sp0; sb.nw = nw;
-    u32 covw[10];
-#pragma unroll 1
-    for (int i = 0; i < 10; i++) covw[i] = 0u;
-    /* coverage for words -1 .. nw (one extra word on each side for the run-boundary tests) */
-#pragma unroll 1
-    for (int i = 0; i < 10; i++)
-        if (i < nw + 2) covw[i] = cov_word(rv, t, sp0 + 32 * (i - 1), lane);
-    const bool raw = (t == 0) && c_prm.raw_hits_A;
-    u32 hs[10];
-#pragma unroll 1
-    for (int i = 0; i < 10; i++) hs[i] = 0u;
-    if (raw) {
-        const ntl_dev_pat &pt = c_prm.main_pat[0];
-#pragma unroll 1
-        for (int i = 0; i < 10; i++)
-            if (i < nw + 1) hs[i] = hits32(rv, pt, 0, -1, sp0 + 32 * (i - 1), 1, rv.L, lane);
-    }
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) {
-        if (i < nw) {
-            const u32 c = covw[i + 1], cp = covw[i], cn = covw[i + 2];
-            sb.cov[i] = c;
-            if (raw) {
-                sb.st[i] = hs[i + 1];
-                sb.en[i] = __funnelshift_l(hs[i], hs[i + 1], c_prm.main_pat[0].m - 1);
-            } else {
-                sb.st[i] = c & ~((c << 1) | (cp >> 31));
-                sb.en[i] = c & ~((c >> 1) | (cn << 31));
-            }
-        } else { sb.cov[i] = 0u; sb.st[i] = 0u; sb.en[i] = 0u; }
-    }
-}
-
-/* smallest / largest position with a set bit inside [lo, hi]; INT_MIN-like -999999999 if none */
-#define NTL_NONE (-999999999)
-__device__ __noinline__ int span_min(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
-{
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) {
-        if (i >= nw) break;
-        const int p0 = sp0 + 32 * i;
-        int lb = lo - p0; if (lb < 0) lb = 0;
-        int hb = hi - p0; if (hb > 31) hb = 31;
-        if (hb < lb) continue;
-        const u32 m = bits[i] & (NTL_FULL >> (31 - hb)) & (NTL_FULL << lb);
-        if (m) return p0 + __ffs((int)m) - 1;
-    }
-    return NTL_NONE;
-}
-__device__ __noinline__ int span_max(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
-{
-#pragma unroll 1
-    for (int i = 7; i >= 0; i--) {
-        if (i >= nw) continue;
-        const int p0 = sp0 + 32 * i;
-        int lb = lo - p0; if (lb < 0) lb = 0;
-        int hb = hi - p0; if (hb > 31) hb = 31;
-        if (hb < lb) continue;
-        const u32 m = bits[i] & (NTL_FULL >> (31 - hb)) & (NTL_FULL << lb);
-        if (m) return p0 + 31 - __clz((int)m);
-    }
-    return NTL_NONE;
-}
-__device__ __noinline__ int span_popc(const u32 (&bits)[8], int sp0, int nw, int lo, int hi)
-{
-    int total = 0;
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) {
-        if (i >= nw) break;
-        const int p0 = sp0 + 32 * i;
-        int lb = lo - p0; if (lb < 0) lb = 0;
-        int hb = hi - p0; if (hb > 31) hb = 31;
-        if (hb < lb) continue;
-        total += __popc(bits[i] & (NTL_FULL >> (31 - hb)) & (NTL_FULL << lb));
-    }
-    return total;
-}
-
-/* get_accurate_end (NanoTel.R:1692-1721) */
+/* get_accurate_end (NanoTel.R:1692-1721).  `ranges` are the raw exact hits of the single fixed pattern on track A
+ * (NanoTel.R:349-354) and the reduced runs of the coverage otherwise (:341-345). */
 __device__ __noinline__ int get_accurate_end(const ReadView &rv, int t, int telo_end, int lane)
 {
     if (telo_end == -1) return -1;
-    SpanBits sb;
-    build_span(rv, t, telo_end - 99, 5, sb, lane);                      /* [e-99, e+60] covers [e-99, e+50] */
+    const int wb = ((telo_end - 99) >> 5) - 1;                           /* lanes 1.. cover [e-99, e+51] */
+    u32 hs;
+    const u32 cov = warp_cov(rv, t, wb, lane, &hs);
+    u32 en;
+    if (t == 0 && c_prm.raw_hits_A) {
+        const u32 hp = __shfl_up_sync(NTL_FULL, hs, 1);
+        en = __funnelshift_l(hp, hs, c_prm.main_pat[0].m - 1);
+    } else {
+        const u32 nx = __shfl_down_sync(NTL_FULL, cov, 1);
+        en = cov & ~((cov >> 1) | (nx << 31));
+    }
     int e_index = telo_end;
-    int m1 = span_max(sb.en, sb.sp0, sb.nw, telo_end - 99, telo_end);
+    const int m1 = lanes_max(en, wb, lane, telo_end - 99, telo_end);
     if (m1 != NTL_NONE) e_index = m1;
-    int m2 = span_max(sb.en, sb.sp0, sb.nw, telo_end + 1, telo_end + 50);
+    const int m2 = lanes_max(en, wb, lane, telo_end + 1, telo_end + 50);
     if (m2 != NTL_NONE) e_index = m2;
     return e_index;
 }
@@ -446,20 +456,27 @@ __device__ __noinline__ int get_accurate_start(const ReadView &rv, int t, int te
 {
     if (telo_start == -1) return telo_start;
     const int s = telo_start;
-    SpanBits sb;
-    build_span(rv, t, s - 36, 5, sb, lane);                             /* [s-36, s+123] covers [s-36, s+99] */
-    const int c50 = span_popc(sb.cov, sb.sp0, sb.nw, s, s + 49);
+    const int wb = ((s - 37) >> 5) - 1;                                  /* lanes 1.. cover [s-37, s+100] */
+    u32 hs;
+    const u32 cov = warp_cov(rv, t, wb, lane, &hs);
+    u32 st;
+    if (t == 0 && c_prm.raw_hits_A) st = hs;
+    else {
+        const u32 pv = __shfl_up_sync(NTL_FULL, cov, 1);
+        st = cov & ~((cov << 1) | (pv >> 31));
+    }
+    const int c50 = lanes_popc(cov, wb, lane, s, s + 49);
     const double first_50 = (double)c50 / 50.0;                         /* IRanges(start, width = 50) :1732 */
     if (first_50 < 0.3) {
-        int a = span_min(sb.st, sb.sp0, sb.nw, s + 48, s + 99);
+        const int a = lanes_min(st, wb, lane, s + 48, s + 99);
         if (a != NTL_NONE) telo_start = a;
-        int b = span_min(sb.st, sb.sp0, sb.nw, s + 33, s + 48);
+        const int b = lanes_min(st, wb, lane, s + 33, s + 48);
         if (b != NTL_NONE) telo_start = b;
     } else {
-        int a = span_min(sb.st, sb.sp0, sb.nw, s, s + 99);
+        const int a = lanes_min(st, wb, lane, s, s + 99);
         if (a != NTL_NONE) telo_start = a;
         if (first_50 >= 0.72) {
-            int b = span_min(sb.st, sb.sp0, sb.nw, s - 36, s - 1);
+            const int b = lanes_min(st, wb, lane, s - 36, s - 1);
             if (b != NTL_NONE) telo_start = b;
         }
     }
@@ -469,7 +486,8 @@ __device__ __noinline__ int get_accurate_start(const ReadView &rv, int t, int te
 /* One 18-bp window of search_left/right_patterns (multi_pattern_step_*, NanoTel.R:496-575, :614, :676):
  * matchPattern on subseq(read, a, b) with the default fixed = TRUE, the window's own out-of-bounds rule, hits not
  * trimmed.  Returns false if no pattern hits. */
-__device__ __noinline__ bool step_window(const ReadView &rv, int a, int b, int k, bool use_tvr, int *min_start, int *max_end, int lane)
+__device__ __noinline__ bool step_window(const ReadView &rv, int a, int b, int k, bool use_tvr, int *min_start,
+                                         int *max_end, int lane)
 {
     bool any = false;
     int mn = 0, mx = 0;
@@ -478,7 +496,7 @@ __device__ __noinline__ bool step_window(const ReadView &rv, int a, int b, int k
         const int kk = pass == 0 ? k : 0;
         for (int p = 0; p < np; p++) {
             const ntl_dev_pat &pt = pass == 0 ? c_prm.main_pat[p] : c_prm.tvr_pat[p];
-            /* alignment starts a - kk .. b - m + 1 + kk : at most 18 - m + 1 + 2 <= 16 + 2 of them */
+            /* alignment starts a - kk .. b - m + 1 + kk : at most 18 - m + 1 + 2 of them */
             const int s0 = a - kk;
             u32 h = hits32(rv, pt, kk, 1, s0, a, b, lane);
             const int nstarts = (b - pt.m + 1 + kk) - s0 + 1;
@@ -531,11 +549,180 @@ __device__ __noinline__ int search_right(const ReadView &rv, int end_index, int 
     return new_end;
 }
 
+/* =============================================================================================================
+ * K3a: triage, one THREAD per read.  A read whose window tables hold no telomeric window on any track takes the
+ * same path through find_telo_position_wraper every time: find_telo_position = (-1,-1) (:1026-1028), the
+ * get_accurate_* calls return -1, width 1 < 100 sends it to find_left/right_telo, which return (-1,-1) as soon as a
+ * window lies beyond max_diff = 200 of the chosen edge (:861, :921), search_right_patterns looks at s[1..18]
+ * (:1141 with end_index 0) and, finding nothing, leaves (-1, 0): width 2 < 30, not telomeric (:1847).  The thread
+ * verifies each of those conditions (integer window classes, one bit-parallel match over the first word) and writes
+ * the record; every other read goes on the candidate list of the warp-per-read locate kernel.
+ * ============================================================================================================= */
+__device__ __forceinline__ bool triage_first_window_hit(u32 lo, u32 hi, int T)
+{
+    /* subseq(read, 1, 18), matchPattern with fixed = TRUE (NanoTel.R:614/:676 via :1141): positions outside the
+     * window are mismatches, alignment starts 1-k .. 18-m+1+k */
+    const u32 vm = 0x7fffeu;                                  /* bits 1..18 */
+    const u32 pA = ~hi & ~lo & vm, pC = ~hi & lo & vm, pG = hi & lo & vm, pT = hi & ~lo & vm;
+    bool any = false;
+    for (int pass = 0; pass < 2; pass++) {
+        const int np = pass == 0 ? c_prm.n_main : (T == 3 ? c_prm.n_tvr : 0);
+        for (int p = 0; p < np; p++) {
+            const ntl_dev_pat &pt = pass == 0 ? c_prm.main_pat[p] : c_prm.tvr_pat[p];
+            u32 ones = 0u, twos = 0u;
+            for (int j = 0; j < pt.m; j++) {
+                const u32 nb = pt.nib[j];
+                const u32 e = nb == 1u ? pA : nb == 2u ? pC : nb == 4u ? pG : nb == 8u ? pT : 0u;
+                const u32 x = ~(e >> j);
+                twos |= ones & x;
+                ones ^= x;
+            }
+            /* exact alignments start in [1, 19-m]; with one mismatch (main patterns on tracks B, C) in [0, 20-m] */
+            const int hi0 = 19 - pt.m;
+            const u32 sm0 = hi0 >= 1 ? ((2u << hi0) - 2u) : 0u;
+            any |= (~(ones | twos) & sm0) != 0u;
+            if (pass == 0) {
+                const int hi1 = 20 - pt.m;
+                const u32 sm1 = hi1 >= 0 ? ((2u << hi1) - 1u) : 0u;
+                any |= (~twos & sm1) != 0u;
+            }
+        }
+    }
+    return any;
+}
+
+__global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool cand = false;
+    int r = -1;
+    if (i < a.n_reads) {
+        r = a.order[i];
+        ntl_read_result *res = reinterpret_cast<ntl_read_result *>(a.results) + r;
+        const int S = c_prm.S, T = c_prm.n_tracks;
+        const int L = a.len[r];
+        const int n_win = ntl_nwin(L, S);
+        const long long wo = a.win_off[r];
+        int status = 0;
+        bool simple = true;
+        if (a.pass != nullptr && a.pass[r] == 0) status = NTL_READ_FILTERED;
+        else {
+            /* long reads go to the warp-per-read kernel: one thread walking thousands of windows would be the
+             * tail of this launch */
+            simple = a.fmt[r] == 0 && n_win >= 1 && n_win <= NTL_TRIAGE_MAX_WIN;
+            if (simple)
+                simple = c_prm.right_edge ? ((n_win >= 2 ? S : L) < L - 200) : (1 + (n_win - 1) * S > 200);
+            if (simple) {
+                /* any window with  !(count / width < min_density)  on any track?  (8 prefixes per 16-byte load;
+                 * every read's window range starts on a multiple of 8 entries) */
+                const int thr_reg = c_prm.thr_reg;
+                const int thr_last = (int)a.thr[L - (n_win - 1) * S];
+                bool tel = false;
+                for (int t = 0; t < T; t++) {
+                    const uint16_t *cm = a.cum[t] + wo;
+                    const uint4 *cv = reinterpret_cast<const uint4 *>(cm);
+                    const int n_reg = n_win - 1;                 /* windows 0 .. n_win-2 have width S */
+                    const int full = n_reg >> 3;
+                    u32 prev = 0u;
+#pragma unroll 4
+                    for (int g = 0; g < full; g++) {
+                        const uint4 v = __ldg(cv + g);
+                        const u32 x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const u32 l16 = x[q] & 0xffffu, h16 = x[q] >> 16;
+                            tel |= (int)((l16 - prev) & 0xffffu) >= thr_reg;
+                            tel |= (int)((h16 - l16) & 0xffffu) >= thr_reg;
+                            prev = h16;
+                        }
+                    }
+                    for (int k = full << 3; k < n_win; k++) {
+                        const u32 cur = cm[k];
+                        tel |= (int)((cur - prev) & 0xffffu) >= (k == n_win - 1 ? thr_last : thr_reg);
+                        prev = cur;
+                    }
+                }
+                simple = !tel;
+            }
+            if (simple) {
+                const u32 *q = a.packed + a.woff[r];
+                simple = !triage_first_window_hit(q[0], q[4], T);
+            }
+            if (!simple) cand = true;
+        }
+        if (!cand) {
+            ntl_read_result o;
+            o.status = status;
+            o.n_win = n_win > 0 ? n_win : 0;
+            for (int t = 0; t < 3; t++) {
+                const bool live = status == 0 && t < T;
+                o.track[t].start = live ? -1 : 0; o.track[t].end = 0; o.track[t].density = 0.0;
+            }
+            o.win_offset = wo;
+            *res = o;
+            if (a.stages != nullptr && status == 0) {
+                ntl_stage s;
+                s.coarse_start = s.coarse_end = s.acc_start = s.acc_end = s.edge_start = s.edge_end = -1;
+                s.acc_density = 0.0;
+                for (int t = 0; t < T; t++) reinterpret_cast<ntl_stage *>(a.stages)[(size_t)r * 3 + t] = s;
+            }
+        }
+    }
+    /* warp-aggregated append to the candidate list */
+    const u32 cm = __ballot_sync(NTL_FULL, cand);
+    if (cm) {
+        int base = 0;
+        const int leader = __ffs((int)cm) - 1;
+        if (lane == leader) base = (int)atomicAdd(&a.counters[0], (u32)__popc(cm));
+        base = __shfl_sync(NTL_FULL, base, leader);
+        if (cand) a.cand[base + __popc(cm & ((1u << lane) - 1u))] = r;
+    }
+}
+
+/* =============================================================================================================
+ * K3b: full locator, one WARP per candidate read (persistent grid, dynamic work counter)
+ * ============================================================================================================= */
+__device__ void locate_read(const ntl_read_args &a, int r, int lane);
+
 __global__ void __launch_bounds__(128) ntl_locate_kernel(const ntl_read_args a)
 {
     const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= a.n_reads) return;
+    const int n_cand = (int)a.counters[0];
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = (int)atomicAdd(&a.counters[1], 1u);
+        i = __shfl_sync(NTL_FULL, i, 0);
+        if (i >= n_cand) break;
+        locate_read(a, a.cand[i], lane);
+    }
+}
+
+/* any window of this track with  !(count / width < min_density)?  256 prefixes per warp-wide 16-byte load, all
+ * loads independent (the window range of a read starts on a multiple of 8 entries and is padded to one) */
+__device__ __noinline__ bool warp_any_telomeric(const WinTab &w, int lane)
+{
+    const uint4 *cv = reinterpret_cast<const uint4 *>(w.cum);
+    const int groups = (w.n + 7) >> 3;
+    bool tel = false;
+    for (int g = lane; g < groups; g += 32) {
+        const uint4 v = __ldg(cv + g);
+        const u32 x[4] = {v.x, v.y, v.z, v.w};
+        u32 prev = g > 0 ? (u32)w.cum[8 * g - 1] : 0u;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = 8 * g + 2 * q;
+            const u32 l16 = x[q] & 0xffffu, h16 = x[q] >> 16;
+            if (k < w.n) tel |= wt_telo_count(w, k, (int)((l16 - prev) & 0xffffu));
+            if (k + 1 < w.n) tel |= wt_telo_count(w, k + 1, (int)((h16 - l16) & 0xffffu));
+            prev = h16;
+        }
+    }
+    return __any_sync(NTL_FULL, tel);
+}
+
+__device__ void locate_read(const ntl_read_args &a, int r, int lane)
+{
     ntl_read_result *res = reinterpret_cast<ntl_read_result *>(a.results) + r;
     ntl_stage *stg = a.stages ? reinterpret_cast<ntl_stage *>(a.stages) + (size_t)r * 3 : nullptr;
 
@@ -557,8 +744,9 @@ __global__ void __launch_bounds__(128) ntl_locate_kernel(const ntl_read_args a)
         for (int t = 0; t < T && !err; t++) {
             WinTab w;
             w.cum = a.cum[t] + a.win_off[r]; w.n = n_win > 0 ? n_win : 0; w.S = S; w.L = rv.L;
-            w.thr_reg = (int)a.thr[S];
+            w.thr_reg = c_prm.thr_reg;
             w.thr_last = w.n > 0 ? (int)a.thr[wt_end(w, w.n - 1) - wt_start(w, w.n - 1) + 1] : 0;
+            w.any = w.n > 0 && warp_any_telomeric(w, lane);
             const int k = t >= 1 ? 1 : 0;
             const bool use_tvr = t == 2;
 
@@ -642,10 +830,21 @@ extern "C" cudaError_t ntl_k_filter(const ntl_read_args *a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-extern "C" cudaError_t ntl_k_locate(const ntl_read_args *a, cudaStream_t st)
+extern "C" cudaError_t ntl_k_triage(const ntl_read_args *a, cudaStream_t st)
 {
     if (a->n_reads <= 0) return cudaSuccess;
-    const int wpb = 4;
-    ntl_locate_kernel<<<(a->n_reads + wpb - 1) / wpb, wpb * 32, 0, st>>>(*a);
+    ntl_triage_kernel<<<(a->n_reads + 255) / 256, 256, 0, st>>>(*a);
     return cudaGetLastError();
+}
+
+extern "C" cudaError_t ntl_k_locate(const ntl_read_args *a, int grid, cudaStream_t st)
+{
+    if (a->n_reads <= 0) return cudaSuccess;
+    ntl_locate_kernel<<<grid, 128, 0, st>>>(*a);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t ntl_k_locate_occupancy(int *blocks_per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ntl_locate_kernel, 128, 0);
 }

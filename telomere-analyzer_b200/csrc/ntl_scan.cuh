@@ -40,6 +40,7 @@ typedef unsigned int u32;
 /* c_prm (__constant__ ntl_dev_params) is defined by the including .cu file before this header */
 #define PRM_S        (c_prm.S)
 #define PRM_NTRACKS  (c_prm.n_tracks)
+#define PRM_THR_REG  (c_prm.thr_reg)
 #define PRM_MAIN_LEN(p) (c_prm.main_pat[p].m)
 #define PRM_TVR_LEN(p)  (c_prm.tvr_pat[p].m)
 #define PRM_NMAIN_GROUPS (c_prm.n_main_groups)
@@ -52,6 +53,7 @@ typedef unsigned int u32;
 #else
 #define PRM_S        NTL_J_S
 #define PRM_NTRACKS  NTL_J_NTRACKS
+#define PRM_THR_REG  NTL_J_THR_REG
 #define PRM_MAIN_LEN(p) (NTL_J_MAIN_LEN[p])
 #define PRM_TVR_LEN(p)  (NTL_J_TVR_LEN[p])
 #define PRM_NMAIN_GROUPS NTL_J_NMAIN_GROUPS

@@ -37,7 +37,7 @@ class Timings(C.Structure):
         ("locate_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
         ("bases", C.c_int64), ("packed_bytes", C.c_int64), ("window_bytes", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-        ("kernel_launches", C.c_int32), ("scan_is_jit", C.c_int32), ("steps", C.c_int32), ("reserved", C.c_int32),
+        ("kernel_launches", C.c_int32), ("scan_is_jit", C.c_int32), ("steps", C.c_int32), ("candidates", C.c_int32),
     ]
 
 
