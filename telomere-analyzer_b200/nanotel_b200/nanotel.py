@@ -1,0 +1,345 @@
+"""Python host mirror of NanoTel.R's interface for the per-read telomere-detection path.
+
+R is not installable in this image, so the host side that `north_star` places in R is mirrored here in Python with
+the reference's own function names, argument meaning and outputs; the R glue a maintainer would use instead is in
+../R/ (INTEGRATION.md).  Every number below comes from libnanotel_b200.so (CUDA); this module only moves data,
+assigns Serial numbers through the library's ntl_assign_serials, and writes the files NanoTel.R writes.
+
+    search_patterns(...)             NanoTel.R:2001-2078   one call = one sequential pass over a read set
+    filter_reads(...)                NanoTel.R:2123-2163
+    run_future_worker_chuncks(...)   NanoTel.R:2171-2268   chunk loop: read --nrec records, rc, filter, 8-way Serial
+    main(argv)                       NanoTel.R:19-99, 2304-2433   same command line flags, same output files
+"""
+from __future__ import annotations
+
+import argparse
+import gzip
+import io
+import os
+import sys
+import time
+from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .scanner import Scanner, assign_serials
+
+VERSION = "Telomere Analyzer  version v1.1.9-beta 2026-02-19 (nanotel_b200 CUDA path)"
+
+Read = Tuple[str, bytes]          # (header line without '>' / '@', sequence) -- one element of a DNAStringSet
+
+SUMMARY_COLUMNS = ["Serial", "sequence_ID", "sequence_length",
+                   "telo_density", "Telomere_start", "Telomere_end", "Telomere_length",
+                   "telo_density_mismatch", "Telomere_start_mismatch", "Telomere_end_mismatch",
+                   "Telomere_length_mismatch"]
+TVR_COLUMNS = ["telo_density_mismatch_tvr", "Telomere_start_mismatch_tvr", "Telomere_end_mismatch_tvr",
+               "Telomere_length_mismatch_tvr"]
+
+
+# ------------------------------------------------------------------------------------------------ input
+def _open_maybe_gzip(path: str):
+    f = open(path, "rb")
+    magic = f.read(2)
+    f.seek(0)
+    if magic == b"\x1f\x8b":
+        return io.BufferedReader(gzip.GzipFile(fileobj=f), 1 << 20)
+    return io.BufferedReader(f, 1 << 20)
+
+
+def iter_records(paths: Sequence[str], fmt: str) -> Iterator[Read]:
+    """readDNAStringSet semantics: FASTA may be multi-line, FASTQ is 4-line records, names are
+    the full header line, qualities are ignored, gzip is transparent."""
+    for p in paths:
+        with _open_maybe_gzip(p) as f:
+            if fmt == "fasta":
+                name, parts = None, []
+                for line in f:
+                    line = line.rstrip(b"\r\n")
+                    if line.startswith(b">"):
+                        if name is not None:
+                            yield name, b"".join(parts)
+                        name, parts = line[1:].decode("utf-8", "replace"), []
+                    elif line and name is not None:
+                        parts.append(line)
+                if name is not None:
+                    yield name, b"".join(parts)
+            elif fmt == "fastq":
+                while True:
+                    h = f.readline()
+                    if not h:
+                        break
+                    s = f.readline().rstrip(b"\r\n")
+                    f.readline()
+                    f.readline()
+                    if not h.startswith(b"@"):
+                        raise ValueError("%s: malformed FASTQ record header %r" % (p, h[:40]))
+                    yield h[1:].rstrip(b"\r\n").decode("utf-8", "replace"), s
+            else:
+                raise ValueError('format should be "fastq" or "fasta"')
+
+
+def list_input_files(input_path: str) -> List[str]:
+    """dir(full.names = TRUE, recursive = TRUE) for a directory, else the file itself (NanoTel.R:2174-2178)."""
+    if os.path.isdir(input_path):
+        out = []
+        for root, _, files in os.walk(input_path):
+            out.extend(os.path.join(root, f) for f in files)
+        return sorted(out)
+    return [input_path]
+
+
+def iter_chunks(paths: Sequence[str], fmt: str, nrec: int) -> Iterator[List[Read]]:
+    """readDNAStringSet(files, nrec = nrec) in a loop (NanoTel.R:2209-2217)."""
+    chunk: List[Read] = []
+    for rec in iter_records(paths, fmt):
+        chunk.append(rec)
+        if nrec > 0 and len(chunk) >= nrec:
+            yield chunk
+            chunk = []
+    if chunk:
+        yield chunk
+
+
+# ------------------------------------------------------------------------------------------------ tables
+def _tokens(p) -> List[str]:
+    if p is None:
+        return []
+    if isinstance(p, str):
+        return p.split()
+    return [str(x) for x in p]
+
+
+def _rows_from_results(reads: Sequence[Read], res: np.ndarray, serial: np.ndarray, order: np.ndarray,
+                       n_tracks: int):
+    """One summary row per kept read (analyze_read's add_row, NanoTel.R:1923-1974), in `order`."""
+    rows = []
+    for i in order:
+        r = res[i]
+        row = [int(serial[i]), reads[i][0], len(reads[i][1])]
+        for t in range(n_tracks):
+            tr = r["track"][t]
+            if int(tr["start"]) == -1:                       # NanoTel.R:1926-1931: NA for this track
+                row += [None, None, None, None]
+            else:
+                row += [float(tr["density"]), int(tr["start"]), int(tr["end"]), int(tr["end"]) - int(tr["start"]) + 1]
+        rows.append(row)
+    return rows
+
+
+def _frame(rows, n_tracks: int):
+    import pandas as pd
+    cols = SUMMARY_COLUMNS + (TVR_COLUMNS if n_tracks == 3 else [])
+    df = pd.DataFrame(rows, columns=cols)
+    for c in cols:
+        if c in ("Serial", "sequence_length") or c.startswith("Telomere_"):
+            df[c] = df[c].astype("Int64")
+    return df
+
+
+def search_patterns(sample_telomeres: Sequence[Read], pattern_list, max_length=1e5, output_dir: Optional[str] = None,
+                    serial_start: int = 1, min_density: float = 0.6, title: str = "Telomeric repeat density",
+                    tvr_patterns=None, right_edge: bool = False, *, subseq_length: int = 100,
+                    scanner: Optional[Scanner] = None, device: int = 0):
+    """NanoTel.R:2001-2078.  `sample_telomeres` are the reads exactly as analyze_read would see them (already
+    reverse-complemented / filtered by the caller, as in the reference).  Returns the summary data frame; when
+    output_dir is given, reads/<Serial>.fasta.gz and density_vectors/read<Serial>.csv are written for every row
+    (the reference writes the FASTA and three plots there, NanoTel.R:1870-1918).  `max_length` and `title` only
+    affect the reference's plots and are accepted for signature parity."""
+    own = scanner is None
+    sc = scanner or Scanner(_tokens(pattern_list), _tokens(tvr_patterns) or None, min_density, subseq_length,
+                            rc=False, use_filter=False, right_edge=right_edge, device=device)
+    try:
+        res = sc.scan([s for _, s in sample_telomeres])
+        keep = (res["status"] & _lib.READ_KEEP) != 0
+        serial = np.zeros(len(res), np.int32)
+        serial[keep] = serial_start + np.arange(int(keep.sum()), dtype=np.int32)   # :2050-2069, one sequential pass
+        order = np.nonzero(keep)[0]
+        rows = _rows_from_results(sample_telomeres, res, serial, order, sc.n_tracks)
+        if output_dir:
+            write_read_outputs(output_dir, sample_telomeres, sc, res, serial, order)
+        return _frame(rows, sc.n_tracks)
+    finally:
+        if own:
+            sc.close()
+
+
+def filter_reads(samples: Sequence[Read], patterns, do_rc: bool = True, num_of_cores: int = 10,
+                 subread_width: int = 200, right_edge: bool = True, trimm_length: int = 70, *,
+                 min_density: float = 0.6, device: int = 0) -> Optional[List[Read]]:
+    """NanoTel.R:2123-2163.  Returns the reads that pass the edge filter (reverse-complemented first if do_rc, as the
+    reference does), or None when none passes (the reference returns NA).  subread_width / trimm_length are fixed at
+    200 / 70 in the kernel, as every call site of the reference uses them (NanoTel.R:2229)."""
+    if subread_width != 200 or trimm_length != 70:
+        raise ValueError("the CUDA edge filter implements the reference's only call: subread_width=200, trimm_length=70")
+    with Scanner(_tokens(patterns), None, min_density, 100, rc=do_rc, use_filter=True, right_edge=right_edge,
+                 device=device) as sc:
+        res = sc.scan([s for _, s in samples])
+    passed = (res["status"] & _lib.READ_FILTERED) == 0
+    out = []
+    for (name, seq), ok in zip(samples, passed):
+        if ok:
+            out.append((name, revcomp(seq) if do_rc else seq))
+    return out or None
+
+
+_COMP = bytes.maketrans(b"ACGTMRWSYKVHDBNacgtmrwsykvhdbn", b"TGCAKYWSRMBDHVNTGCAKYWSRMBDHVN")
+
+
+def revcomp(seq: bytes) -> bytes:
+    """Biostrings::reverseComplement (IUPAC aware, upper-case result) -- used only to WRITE reads/<Serial>.fasta.gz in
+    the frame NanoTel.R writes them (NanoTel.R:2219-2221 then :1873); the scan itself complements on the fly."""
+    return seq.translate(_COMP)[::-1]
+
+
+# ------------------------------------------------------------------------------------------------ outputs
+def _fmt_double(x: float) -> str:
+    return repr(float(x))            # shortest round-trip representation, as readr::write_csv prints doubles
+
+
+def write_summary_csv(df, path: str) -> None:
+    """readr::write_csv(df_summary) (NanoTel.R:2431-2432): NA for missing, integers plain, doubles shortest."""
+    import csv
+    with open(path, "w", newline="") as f:
+        w = csv.writer(f, quoting=csv.QUOTE_MINIMAL, lineterminator="\n")
+        w.writerow(list(df.columns))
+        for row in df.itertuples(index=False):
+            out = []
+            for v in row:
+                if v is None or v is np.nan or (hasattr(v, "__class__") and v.__class__.__name__ == "NAType"):
+                    out.append("NA")
+                elif isinstance(v, float):
+                    out.append("NA" if v != v else _fmt_double(v))
+                else:
+                    out.append(str(v))
+            w.writerow(out)
+
+
+def write_read_outputs(output_dir: str, reads: Sequence[Read], sc: Scanner, res: np.ndarray, serial: np.ndarray,
+                       order: Iterable[int], rc_applied: bool = False) -> None:
+    """Per telomeric read: reads/<Serial>.fasta.gz (writeXStringSet(compress = TRUE), NanoTel.R:1870-1873) and the
+    per-window tables of every track (the `subs` data frames the plot functions receive, NanoTel.R:1876-1918) as
+    density_vectors/read<Serial>.csv.  Plot rendering itself stays with the reference's R functions."""
+    rd = os.path.join(output_dir, "reads")
+    dv = os.path.join(output_dir, "density_vectors")
+    os.makedirs(rd, exist_ok=True)
+    os.makedirs(dv, exist_ok=True)
+    min_density = sc.params.min_density
+    for i in order:
+        name, seq = reads[i]
+        if rc_applied:
+            seq = revcomp(seq)
+        s = int(serial[i])
+        with gzip.open(os.path.join(rd, "%d.fasta.gz" % s), "wb") as f:
+            f.write(b">" + name.encode() + b"\n")
+            up = seq.upper()
+            for k in range(0, len(up), 80):
+                f.write(up[k:k + 80] + b"\n")
+        cols, header = [], ["ID", "start_index", "end_index"]
+        for t, suffix in zip(range(sc.n_tracks), ("", "_mismatch", "_mismatch_tvr")):
+            st, en, cov, den = sc.windows(int(i), t, int(res[i]["n_win"]))
+            cls = np.where(den < min_density, np.where(den < 0.1, 0, 1), -5)        # NanoTel.R:749-758
+            if t == 0:
+                cols += [np.arange(1, len(st) + 1), st, en]
+            cols += [den, cls]
+            header += ["density" + suffix, "class" + suffix]
+        with open(os.path.join(dv, "read%d.csv" % s), "w") as f:
+            f.write(",".join(header) + "\n")
+            for row in zip(*cols):
+                f.write(",".join(_fmt_double(v) if isinstance(v, (float, np.floating)) else str(int(v)) for v in row) + "\n")
+
+
+# ------------------------------------------------------------------------------------------------ chunk loop
+def run_future_worker_chuncks(input_path: str, output_path: Optional[str], format: str = "fastq", nrec: int = 10000,
+                              patterns=None, do_rc: bool = False, use_filter: bool = False, right_edge: bool = True,
+                              tvr_patterns=None, *, min_density: float = 0.6, subseq_length: int = 100,
+                              device: int = 0, verbose: bool = True):
+    """NanoTel.R:2171-2268.  The 8 forked search_patterns() futures of the reference are replaced by one
+    ntl_scan_batch() per chunk; Serial numbers and row order follow the reference's 8-way round-robin split
+    (ntl_assign_serials).  Returns {"df_summary": DataFrame, "all_reads_length_vec": int array}."""
+    files = list_input_files(input_path)
+    all_len: List[np.ndarray] = []
+    rows = []
+    serial_start = 1
+    with Scanner(_tokens(patterns), _tokens(tvr_patterns) or None, min_density, subseq_length, rc=do_rc,
+                 use_filter=use_filter, right_edge=right_edge, device=device) as sc:
+        for ci, chunk in enumerate(iter_chunks(files, format, nrec), 1):
+            if verbose:
+                print(time.strftime("%Y-%m-%d %H:%M:%S"))
+                print("processing chunk", ci, "...")
+            seqs = [s for _, s in chunk]
+            all_len.append(np.fromiter((len(s) for s in seqs), np.int64, len(seqs)))   # :2225 (before the filter)
+            res = sc.scan(seqs)
+            serial, order, serial_start = assign_serials(res, serial_start)             # :2234-2258
+            rows += _rows_from_results(chunk, res, serial, order, sc.n_tracks)
+            if output_path:
+                write_read_outputs(output_path, chunk, sc, res, serial, order, rc_applied=do_rc)
+        n_tracks = sc.n_tracks
+    return {"df_summary": _frame(rows, n_tracks),
+            "all_reads_length_vec": np.concatenate(all_len) if all_len else np.zeros(0, np.int64)}
+
+
+# ------------------------------------------------------------------------------------------------ command line
+def build_parser() -> argparse.ArgumentParser:
+    """The option list of NanoTel.R:30-92 (optparse), same names and defaults."""
+    ap = argparse.ArgumentParser(prog="NanoTel", description="Telomere pattern finder (CUDA hot path)")
+    ap.add_argument("-i", "--input_path", default=None, help="Path to input files.( dir or single file)")
+    ap.add_argument("--save_path", default=None, help="A path to a directory for storing the output files.")
+    ap.add_argument("--format", default="fastq", help='input files format ("fastq" (the default) or "fasta", gzip is supported)')
+    ap.add_argument("-n", "--nrec", type=int, default=10000, help="maximum number of records to read per iteration")
+    ap.add_argument("-r", "--rc", action="store_true", default=False, help="reverse complement the given reads")
+    ap.add_argument("--patterns", default=None, help="Space separated list of pattern(s). Must be in double quotes.")
+    ap.add_argument("--min_density", type=float, default=0.6)
+    ap.add_argument("--subseq_length", type=int, default=100)
+    ap.add_argument("--use_filter", action="store_true", default=False)
+    ap.add_argument("--check_right_edge", action="store_true", default=False)
+    ap.add_argument("--tvr_patterns", default=None)
+    ap.add_argument("--version", action="store_true", default=False)
+    ap.add_argument("--analysis", action="store_true", default=False,
+                    help="post-processing of the reference (NanoTel.R:2438-2508) -- not part of the CUDA path")
+    ap.add_argument("--device", type=int, default=0, help="CUDA device ordinal (extension)")
+    return ap
+
+
+def main(argv: Optional[Sequence[str]] = None) -> int:
+    opt = build_parser().parse_args(argv)
+    if opt.version:
+        print(VERSION)
+        return 0
+    if opt.patterns is None:
+        sys.exit("Missing required parameter:  --patterns")
+    if opt.save_path is None:
+        sys.exit("Missing required parameter:  --save_path")
+    if opt.input_path is None:
+        sys.exit("Missing required parameter:  --input_path")
+    os.makedirs(opt.save_path, exist_ok=True)
+    t1 = time.time()
+    ans = run_future_worker_chuncks(opt.input_path, opt.save_path, opt.format, opt.nrec, opt.patterns, opt.rc,
+                                    opt.use_filter, opt.check_right_edge, opt.tvr_patterns,
+                                    min_density=opt.min_density, subseq_length=opt.subseq_length, device=opt.device)
+    df = ans["df_summary"]
+    barcode_name = os.path.basename(os.path.normpath(opt.input_path))
+    write_summary_csv(df, os.path.join(opt.save_path, barcode_name + "_summary.csv"))        # :2430-2432
+    with open(os.path.join(opt.save_path, "reads_ids.txt"), "w") as f:                        # :2433
+        for sid in df["sequence_ID"]:
+            f.write(str(sid) + "\n")
+    lens = ans["all_reads_length_vec"]
+    os.makedirs(os.path.join(opt.save_path, "log"), exist_ok=True)
+    with open(os.path.join(opt.save_path, "log", "run.log"), "w") as f:
+        f.write(VERSION + "\n")
+        f.write("The patterns to search: %s\n" % opt.patterns)
+        f.write("The sub-sequence length  is: %d\n" % opt.subseq_length)
+        f.write("The minimal density for a telomeric subseq: %s\n" % opt.min_density)
+        f.write("Total reads in sample: %d\n" % len(lens))
+        f.write("Number of reads which identified as Telomeric: %d\n" % len(df))
+        if len(lens):
+            f.write("%% of total reads: %s%%\n" % round(100.0 * len(df) / len(lens), 2))
+        f.write("Elapsed: %.3f s\n" % (time.time() - t1))
+    if opt.analysis:
+        print("--analysis is the reference's downstream post-processing (NanoTel.R:2438-2508); it is outside the "
+              "CUDA hot path and not implemented here", file=sys.stderr)
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

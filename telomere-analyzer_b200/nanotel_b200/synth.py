@@ -71,8 +71,8 @@ def _tract(rng: np.random.Generator, length: int, g_strand: bool, tvr: bool) -> 
             u = units[int(rng.integers(0, 4))]
             parts.append(np.frombuffer(u, np.uint8))
             tot += len(u)
-        z = np.concatenate(parts)[:zone]
-        raw[:len(z)] = z                      # proximal (centromere side) boundary of a G-strand tract is its start
+        z = np.concatenate(parts)[:min(zone, len(raw))]
+        raw[:len(z)] = z                     # proximal (centromere side) boundary of a G-strand tract is its start
     seq = _with_errors(rng, raw)
     if len(seq) < length:
         seq = np.concatenate([seq, _repeat(b"TTAGGG", length - len(seq), 0)])
@@ -95,7 +95,7 @@ def synth_reads(n_reads: int, seed: int, telomeric_frac: float = 0.10, median_le
     kinds = np.zeros(n_reads, np.int8)          # 0 none, 1 G-strand at 3' end, 2 C-strand at 5' end, 3 interstitial
     for i in np.nonzero(is_telo)[0]:
         L = int(lens[i])
-        t = int(np.clip(np.exp(rng.normal(np.log(6000.0), 0.6)), 200, 0.8 * L))
+        t = int(min(max(np.exp(rng.normal(np.log(6000.0), 0.6)), 200.0), max(0.8 * L, 1.0)))
         g = bool(rng.random() < 0.5)
         tvr = bool(rng.random() < 0.3)
         adapter = int(rng.integers(0, 81))

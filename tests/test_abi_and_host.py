@@ -1,0 +1,131 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol include/nanotel_b200.h declares,
+struct layouts match, the NVRTC specialisation compiles for sm_100a without a device, compute entry points fail loudly
+without a GPU (no CPU fallback), and the host-side Serial / window logic equals the oracle's restatement."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from nanotel_b200 import _lib
+    return _lib, _lib.load()
+
+
+def test_every_declared_symbol_is_exported():
+    _l, L = _lib()
+    hdr = open(os.path.join(ROOT, "include", "nanotel_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ntl_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 19
+    for sym in sorted(declared):
+        assert hasattr(L, sym), "libnanotel_b200.so does not export %s" % sym
+    assert declared == set(_l.EXPORTS), declared ^ set(_l.EXPORTS)
+    assert L.ntl_version() == 100
+
+
+def test_struct_layouts():
+    _l, L = _lib()
+    assert _l.RESULT_DTYPE.itemsize == 64
+    assert C.sizeof(_l.Stage) == 32
+    assert C.sizeof(_l.Timings) == 7 * 8 + 5 * 8 + 4 * 4
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from nanotel_b200 import NanoTelError, Scanner
+    with pytest.raises(NanoTelError) as e:
+        Scanner("TTAGGG")
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("pats,tvr,S", [("TTAGGG", None, 100), ("YYAGGG", "TTGGG CCAGGG TCAGGG", 100),
+                                         ("CCCTAA CCCTGA", "CCCAA", 500), ("N", None, 7), ("ACGTACGTACGTACGTAC", None, 200)])
+def test_nvrtc_specialisation_compiles_for_sm_100a(pats, tvr, S, tmp_path):
+    _l, L = _lib()
+    P = _l.make_params(pats, tvr, subseq_length=S, rc=True)
+    log = C.create_string_buffer(1 << 16)
+    cubin = str(tmp_path / "k.cubin").encode()
+    n = L.ntl_jit_compile_check(C.byref(P), b"sm_100a", log, 1 << 16, cubin)
+    assert n > 1000, log.value.decode(errors="replace")
+    assert os.path.getsize(cubin) == n
+
+
+@pytest.mark.parametrize("bad,code", [((["TTAGGG", ""], None), -2), (("TTAGGX", None), -2), (("A" * 19, None), -2),
+                                      (("TTAGGG", "TT-GG"), -2)])
+def test_pattern_validation(bad, code):
+    _l, L = _lib()
+    P = _l.make_params(bad[0], bad[1])
+    log = C.create_string_buffer(4096)
+    assert L.ntl_jit_compile_check(C.byref(P), b"sm_100a", log, 4096, None) == code
+
+
+def test_count_windows_matches_split_telo():
+    from nanotel_b200 import count_windows
+    from oracle import oracle as O
+    rng = np.random.default_rng(1)
+    for S in (1, 7, 20, 64, 100, 128, 200, 500, 4096):
+        for L in list(range(1, 40)) + rng.integers(1, 300000, 200).tolist():
+            assert count_windows(L, S) == O.count_windows(L, S), (L, S)
+
+
+def test_assign_serials_follows_the_8_way_split():
+    """NanoTel.R:2234-2258 against the oracle's restatement, incl. gaps, the < 8 sequential branch and filtering."""
+    from nanotel_b200 import READ_FILTERED, READ_KEEP, RESULT_DTYPE, assign_serials
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    for n in [0, 1, 5, 7, 8, 9, 16, 17, 100, 1001]:
+        for trial in range(4):
+            res = np.zeros(n, RESULT_DTYPE)
+            keep = rng.random(n) < 0.4
+            filt = rng.random(n) < (0.3 if trial % 2 else 0.0)
+            res["status"] = np.where(filt, READ_FILTERED, np.where(keep, READ_KEEP, 0))
+            start = int(rng.integers(1, 50))
+            serial, order, nxt = assign_serials(res, start)
+            idx = np.nonzero(~filt)[0]
+            o_serial, o_order, o_next, _ = O.assign_serials((keep & ~filt)[idx].astype(np.int32), start, start - 1)
+            exp = np.zeros(n, np.int32)
+            exp[idx] = o_serial
+            assert np.array_equal(serial, exp)
+            assert np.array_equal(order, idx[o_order])
+            assert nxt == o_next
+    # worked example: 10 reads, all kept -> groups {0,8},{1,9},{2},...; group g starts at serial_start + sum of sizes
+    res = np.zeros(10, RESULT_DTYPE)
+    res["status"] = READ_KEEP
+    serial, order, nxt = assign_serials(res, 1)
+    assert serial.tolist() == [1, 3, 5, 6, 7, 8, 9, 10, 2, 4]
+    assert order.tolist() == [0, 8, 1, 9, 2, 3, 4, 5, 6, 7] and nxt == 11
+
+
+def test_fasta_fastq_reader_and_chunking(tmp_path):
+    import gzip
+    from nanotel_b200.nanotel import iter_chunks, list_input_files, revcomp
+    fa = tmp_path / "a.fasta"
+    fa.write_text(">r1 desc\nACGT\nAC\n>r2\nTTAGGG\n")
+    fq = tmp_path / "b.fastq.gz"
+    with gzip.open(fq, "wt") as f:
+        f.write("@q1 x\nACGTN\n+\nIIIII\n@q2\nGG\n+\nII\n")
+    assert [c for c in iter_chunks([str(fa)], "fasta", 1)] == [[("r1 desc", b"ACGTAC")], [("r2", b"TTAGGG")]]
+    assert [c for c in iter_chunks([str(fq)], "fastq", 10)] == [[("q1 x", b"ACGTN"), ("q2", b"GG")]]
+    assert list_input_files(str(tmp_path)) == sorted([str(fa), str(fq)])
+    from oracle import oracle as O
+    for s in (b"ACGTNRYKMacgtn", b"TTAGGG"):
+        assert revcomp(s) == O.revcomp(s)
+
+
+def test_shard_bounds_cover_and_balance():
+    from nanotel_b200.shard import shard_bounds
+    rng = np.random.default_rng(0)
+    lens = rng.integers(1000, 250000, 5000)
+    for w in (1, 2, 4, 8):
+        b = shard_bounds(lens, w)
+        assert b[0][0] == 0 and b[-1][1] == len(lens)
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        per = [int(lens[s:e].sum()) for s, e in b]
+        assert max(per) - min(per) <= 2 * 250000

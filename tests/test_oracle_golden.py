@@ -1,0 +1,134 @@
+"""Pin the oracle against every known-answer artefact the reference ships for this path:
+
+* Example/Example_output/summary.csv (2023): start / end / length / density of both tracks for the 4 example reads.
+  The example pre-dates the search_left/right_patterns refinement (NanoTel.R:1140-1152), so it pins the stage right
+  after get_accurate_start/end (NanoTel.R:1126) -- `acc_*` of the oracle -- and the density arithmetic there.
+* single_read_plots_adj/read1.eps: the per-window density vectors of read 1, tracks A and B.
+* the matchPattern example written in NanoTel.R:273-302 (right-hand out-of-bounds hit and trim()).
+Everything after NanoTel.R:1126 has no golden data anywhere: tested below only as restatement regression values
+(an independent throw-away restatement) and marked as such.
+"""
+import csv
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_summary_csv_2023_is_reproduced_at_the_get_accurate_stage(example_reads):
+    rows = list(csv.DictReader(open(os.path.join(GOLD, "example_summary_2023.csv"))))
+    assert len(rows) == 4
+    P = O.make_params("TTAGGG", None, 0.6, 100, False)          # README.md:79 command
+    for (name, seq), g in zip(example_reads, rows):
+        r = O.analyze_read(P, seq).rec
+        assert name == g["sequence_ID"] and len(seq) == int(g["sequence_length"])
+        assert r["keep"] == 1
+        for t, sfx in ((0, ""), (1, "_mismatch")):
+            tr = r["t"][t]
+            assert int(tr["acc_start"]) == int(g["Telomere_start" + sfx])
+            assert int(tr["acc_end"]) == int(g["Telomere_end" + sfx])
+            assert int(tr["acc_end"]) - int(tr["acc_start"]) + 1 == int(g["Telomere_length" + sfx])
+            assert repr(float(tr["acc_density"])) == g["telo_density" + sfx]      # all 16 printed digits
+
+
+def test_eps_window_densities_of_read1(example_reads):
+    fx = json.load(open(os.path.join(GOLD, "example_read1_eps_density.json")))
+    seq = example_reads[0][1]
+    res = O.analyze_read(O.make_params("TTAGGG"), seq)
+    st, en = O.split_telo(len(seq), 100)
+    assert len(st) == 30
+    for t, key in ((0, "exact"), (1, "mismatch")):
+        y = fx["tracks"][key]["y"]
+        # polygon(y = c(0, density, last(density), 0)) NanoTel.R:1331-1338
+        assert len(y) == 30 + 3 and y[0] == 0.0 and abs(y[-1]) < 1e-4
+        dens = res.win_counts[t] / (en - st + 1)
+        np.testing.assert_allclose(dens, y[1:31], atol=0.6 / 344.0)   # 0.01 pt resolution, accumulated
+        assert abs(y[31] - dens[-1]) < 0.6 / 344.0
+
+
+def test_matchpattern_example_from_the_reference_comments():
+    # NanoTel.R:273-302: matchPattern("ATGG", "AATGCGCGTGGATATG", max.mismatch = 1) -> starts 2, 8, 14; the last one
+    # ends at 17 > 16 (out of bounds) and trim() clips it to [14, 16].
+    starts = O.match_pattern(b"AATGCGCGTGGATATG", "ATGG", 1, True)
+    assert starts.tolist() == [2, 8, 14]
+    assert O.match_pattern(b"AATGCGCGTGGATATG", "ATGG", 0, True).tolist() == []
+
+
+def test_left_out_of_bounds_hit_is_symmetric():
+    # assumed from the Biostrings documentation: no artefact of the reference exercises it
+    assert O.match_pattern(b"TAGGGTTAGGG", "TTAGGG", 1, True).tolist() == [0, 6]
+
+
+@pytest.mark.parametrize("length,S,expected", [
+    (2981, 100, 30), (20410, 100, 204), (59430, 100, 594), (15880, 100, 159),
+    (120, 100, 1), (150, 100, 1), (151, 100, 2), (50, 100, 0), (51, 100, 1), (100, 100, 1), (1, 100, 0),
+    (20410, 200, 102), (20410, 500, 41), (249, 500, 0), (251, 500, 1),
+])
+def test_split_telo(length, S, expected):
+    assert O.count_windows(length, S) == expected
+    st, en = O.split_telo(length, S)
+    assert len(st) == expected
+    if expected:
+        assert st[0] == 1 and en[-1] == length
+        assert np.all(st[1:] == en[:-1] + 1)
+        assert np.all(en[:-1] - st[:-1] + 1 == S)
+        assert S / 2 <= en[-1] - st[-1] + 1 < S + S / 2 + 1
+
+
+# ---- restatement regression values (SURVEY App. C "final values per the current code"): NOT confirmed by any R run
+APP_C = {
+    ("TTAGGG", None, 100): [
+        [(0.9919354838709677, 1, 2976), (0.9976517946997652, 1, 2981)],
+        [(0.9630518234165067, 12070, 20405), (0.9743309666848716, 11251, 20405)],
+        [(0.9837031219320637, 49241, 59426), (0.9906408174959411, 48956, 59426)],
+        [(0.9705955437753665, 3805, 15877), (0.9874927524227616, 3805, 15877)]],
+    ("YYAGGG", None, 100): [
+        [(0.9916022841787034, 1, 2977), (0.9976517946997652, 1, 2981)],
+        [(0.9698649951783992, 12111, 20406), (0.9755990808622388, 11268, 20406)],
+        [(0.9824762999138179, 48985, 59427), (0.9913726993865031, 48996, 59427)],
+        [(0.9715090276627464, 3805, 15878), (0.9879079012754679, 3805, 15878)]],
+    ("YYAGGG", "TTGGG CCAGGG TCAGGG", 100): [
+        [None, None, (0.9976517946997652, 1, 2981)],
+        [None, None, (0.9766932924827662, 11268, 20406)],
+        [None, None, (0.9913726993865031, 48996, 59427)],
+        [None, None, (0.9887361272155044, 3805, 15878)]],
+    ("TTAGGG TTGGG", None, 100): [
+        [(0.9936155913978495, 1, 2976), (0.9976517946997652, 1, 2981)],
+        [(0.9622552488794527, 11928, 20405), (0.9765437486362645, 11240, 20405)],
+        [(0.9869513641755635, 49311, 59426), (0.9906408174959411, 48956, 59426)],
+        [(0.9730804273999835, 3805, 15877), (0.9894806593224551, 3805, 15877)]],
+    ("TTAGGG", None, 500): [
+        [(0.9919354838709677, 1, 2976), (0.9976517946997652, 1, 2981)],
+        [(0.9574694941357659, 11965, 20405), (0.9776780706674145, 11491, 20405)],
+        [(0.9752650176678446, 48956, 59426), (0.9906408174959411, 48956, 59426)],
+        [(0.9733837111670864, 3968, 15877), (0.9879862219608502, 3975, 15877)]],
+}
+
+
+@pytest.mark.parametrize("key", sorted(APP_C, key=str), ids=lambda k: "%s|%s|S%d" % k)
+def test_final_values_match_the_independent_restatement(example_reads, key):
+    pats, tvr, S = key
+    P = O.make_params(pats, tvr, 0.6, S, False)
+    for (name, seq), exp in zip(example_reads, APP_C[key]):
+        r = O.analyze_read(P, seq).rec
+        for t, e in enumerate(exp):
+            if e is None:
+                continue
+            tr = r["t"][t]
+            assert (repr(float(tr["density"])), int(tr["start"]), int(tr["end"])) == (repr(e[0]), e[1], e[2])
+
+
+def test_range_list_kind_follows_the_reference():
+    # NanoTel.R:347-354: one fixed pattern keeps the raw hit list on the exact track; everything else is reduced.
+    seq = None
+    for line in open(os.path.join(GOLD, "sample.fasta"), "rb").read().split(b">")[1:2]:
+        seq = line.split(b"\n", 1)[1].replace(b"\n", b"")
+    n_raw = O.analyze_read(O.make_params("TTAGGG"), seq).rec["t"][0]["n_ranges"]
+    n_list = O.analyze_read(O.make_params("TTAGGG TTAGGG"), seq).rec["t"][0]["n_ranges"]
+    n_iupac = O.analyze_read(O.make_params("YYAGGG"), seq).rec["t"][0]["n_ranges"]
+    assert n_raw == 492 and n_list < 20 and n_iupac < 20          # 492 raw hits vs a few merged runs
