@@ -112,6 +112,13 @@ __device__ __forceinline__ void ntl_group3(int n, u32 a, u32 b, u32 c, u32 &ex, 
 __device__ __forceinline__ void ntl_dilate5(u32 (&d)[5], int m)
 {
     int w = 1;
+    while (3 * w <= m) {            /* width w -> 3 w: two shifts and one three-input OR (a single LOP3) per word */
+#pragma unroll
+        for (int i = 4; i >= 1; i--)
+            d[i] = d[i] | __funnelshift_l(d[i - 1], d[i], w) | __funnelshift_l(d[i - 1], d[i], 2 * w);
+        d[0] = d[0] | (d[0] << w) | (d[0] << (2 * w));
+        w *= 3;
+    }
     while (2 * w <= m) {
 #pragma unroll
         for (int i = 4; i >= 1; i--) d[i] |= __funnelshift_l(d[i - 1], d[i], w);
@@ -355,15 +362,19 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
                 rel = L - pos0; idx = n_win - 1;
                 act = rel >= 0 && rel < NTL_LANE_BITS;
             }
-            if (act) {
-                const int wi = rel >> 5;
+            {
+                /* branch-free: word (rel >> 5) of the lane's four is picked with clamped funnel shifts */
+                const int wi = (rel >> 5) & 3;
                 const u32 bm = NTL_FULL >> (31 - (rel & 31));
+                const int sh1 = (wi & 1) << 5, sh2 = (wi & 2) << 4;
 #pragma unroll
                 for (int t = 0; t < 3; t++) {
                     if (t < T) {
-                        const u32 wv = wi == 0 ? cov[t][0] : wi == 1 ? cov[t][1] : wi == 2 ? cov[t][2] : cov[t][3];
+                        const u32 wv = __funnelshift_rc(__funnelshift_rc(cov[t][0], cov[t][1], sh1),
+                                                        __funnelshift_rc(cov[t][2], cov[t][3], sh1), sh2);
                         const u32 bf = (pre[t] >> (8 * wi)) & 0xffu;
-                        a.cum[t][wo + idx] = (uint16_t)(ex[t] + bf + (u32)__popc(wv & bm));
+                        const u32 val = ex[t] + bf + (u32)__popc(wv & bm);
+                        if (act) a.cum[t][wo + idx] = (uint16_t)val;
                     }
                 }
             }
