@@ -158,6 +158,10 @@ int ntl_get_stages(const ntl_ctx *ctx, int32_t read_idx, int32_t track, ntl_stag
  * write the cubin to cubin_path (for cuobjdump).  Returns the cubin size in bytes or a negative ntl_status. */
 long ntl_jit_compile_check(const ntl_params *params, const char *arch, char *log, int log_cap,
                            const char *cubin_path);
+/* Pack ONE read exactly as ntl_batch_pack does (no device needed): writes the quads to `words` (capacity in
+ * 32-bit words) and returns the number of words written, negative on error; *four_bit = 1 if the read holds a
+ * letter other than A/C/G/T and was packed as four planes.  Layout: telomere-analyzer_b200/csrc/ntl_dev.h. */
+long ntl_pack_read(const char *seq, int64_t len, int32_t rc, uint32_t *words, int64_t capacity, int32_t *four_bit);
 
 /* -- host-side helpers of the same path ------------------------------------------------------------------- */
 /* Serial numbers and row order of one chunk exactly as search_patterns + the 8-way split assign them

@@ -11,7 +11,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -301,6 +303,20 @@ extern "C" int ntl_create(ntl_ctx **out, const ntl_params *p)
     return NTL_OK;
 }
 
+/* Diagnostics (no device needed): the host packer on one read. */
+extern "C" long ntl_pack_read(const char *seq, int64_t len, int32_t rc, uint32_t *words, int64_t capacity, int32_t *four_bit)
+{
+    if (!seq || !words || len < 1 || len > (1LL << 30)) return NTL_ERR_ARG;
+    const int64_t quads = ((((len >> 5) + 1) + 3) >> 2);
+    if (four_bit) *four_bit = 0;
+    if (capacity < quads * 8) return NTL_ERR_NOMEM;
+    if (ntl_pack_read_2bit(seq, len, rc ? 1 : 0, words) == 0) return (long)(quads * 8);
+    if (capacity < quads * 16) return NTL_ERR_NOMEM;
+    if (ntl_pack_read_4bit(seq, len, rc ? 1 : 0, words) != 0) return NTL_ERR_SEQUENCE;
+    if (four_bit) *four_bit = 1;
+    return (long)(quads * 16);
+}
+
 /* Diagnostics (no device needed): NVRTC-compile the specialised scan kernel for `arch`, optionally saving the cubin. */
 extern "C" long ntl_jit_compile_check(const ntl_params *p, const char *arch, char *log, int log_cap, const char *cubin_path)
 {
@@ -335,7 +351,24 @@ extern "C" void ntl_destroy(ntl_ctx *c)
 }
 
 /* ============================================================================================== pack */
-extern "C" int ntl_batch_pack(ntl_ctx *c, const char *const *seq, const int64_t *len, int32_t n)
+static int ensure_device_buffers(ntl_ctx *c, int64_t packed_words)
+{
+    const int32_t n = c->n_reads;
+    const int T = c->dev.n_tracks;
+    CK(c, c->d_packed.ensure((size_t)packed_words * 4 + 64));
+    CK(c, c->d_meta.ensure(c->meta_bytes + 16));
+    CK(c, c->d_results.ensure((size_t)n * sizeof(ntl_read_result) + 64));
+    CK(c, c->d_cum.ensure((size_t)c->total_windows * 2 * T + 64));
+    CK(c, c->d_pass.ensure((size_t)n + 64));
+    CK(c, c->d_flags.ensure((size_t)n * 4 + 64));         /* candidate list of the locate kernel */
+    if (c->dev.debug_stages) CK(c, c->d_stages.ensure((size_t)n * 3 * sizeof(ntl_stage) + 64));
+    return NTL_OK;
+}
+
+/* overlap = true: the packed words are copied to the device in 16 MiB pieces while the remaining reads are still
+ * being packed (the calling thread issues the copies between its own grains), so that PCIe time hides behind the
+ * packer; the batch ends up in state UPLOADED. */
+static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len, int32_t n, bool overlap)
 {
     if (!c) return NTL_ERR_ARG;
     if (!seq || !len || n < 0) return fail(c, NTL_ERR_ARG, "ntl_batch_pack: bad arguments");
@@ -386,14 +419,58 @@ extern "C" int ntl_batch_pack(ntl_ctx *c, const char *const *seq, const int64_t 
     /* ---- 2-bit packing, all host threads; reads with other letters are queued for the 4-bit arena */
     std::vector<int32_t> iupac;
     std::mutex mu;
-    ntl_parallel_for(n, c->host_threads, 64, [&](int64_t b, int64_t e) {
+    auto pack_range = [&](int64_t b, int64_t e) {
         for (int64_t i = b; i < e; i++) {
             if (ntl_pack_read_2bit(seq[i], len[i], rcflag, hp + h_woff[i]) != 0) {
                 std::lock_guard<std::mutex> g(mu);
                 iupac.push_back((int32_t)i);
             }
         }
-    });
+    };
+    int64_t up_words = 0;                      /* words already handed to cudaMemcpyAsync (overlap mode) */
+    if (!overlap) {
+        ntl_parallel_for(n, c->host_threads, 64, pack_range);
+    } else {
+        c->meta_bytes = off;
+        int rc0 = ensure_device_buffers(c, main_words);
+        if (rc0 != NTL_OK) return rc0;
+        CK(c, cudaEventRecord(c->ev[0], c->stream));
+        const int64_t grain = 64, ngr = (n + grain - 1) / grain;
+        const int64_t piece = 4 << 20;          /* 16 MiB */
+        std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[(size_t)ngr + 1]);
+        for (int64_t g = 0; g <= ngr; g++) done[g].store(0, std::memory_order_relaxed);
+        std::atomic<int64_t> next(0);
+        auto do_grain = [&](int64_t g) {
+            pack_range(g * grain, std::min<int64_t>(n, (g + 1) * grain));
+            done[g].store(1, std::memory_order_release);
+        };
+        auto worker = [&]() {
+            for (;;) {
+                const int64_t g = next.fetch_add(1);
+                if (g >= ngr) break;
+                do_grain(g);
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < c->host_threads && t < ngr; t++) th.emplace_back(worker);
+        cudaError_t cerr = cudaSuccess;
+        int64_t uf = 0;
+        for (;;) {
+            while (uf < ngr && done[uf].load(std::memory_order_acquire)) uf++;
+            const int64_t fw = uf == ngr ? main_words : h_woff[uf * grain];
+            if (cerr == cudaSuccess && (fw - up_words >= piece || (uf == ngr && fw > up_words))) {
+                cerr = cudaMemcpyAsync((uint32_t *)c->d_packed.p + up_words, hp + up_words, (size_t)(fw - up_words) * 4,
+                                       cudaMemcpyHostToDevice, c->stream);
+                up_words = fw;
+            }
+            if (uf == ngr) break;
+            const int64_t g = next.fetch_add(1);
+            if (g < ngr) do_grain(g);
+            else std::this_thread::yield();
+        }
+        for (auto &t : th) t.join();
+        if (cerr != cudaSuccess) return fail(c, NTL_ERR_CUDA, "cudaMemcpyAsync (packed reads) failed: %s", cudaGetErrorString(cerr));
+    }
     if (!iupac.empty()) {
         std::sort(iupac.begin(), iupac.end());
         std::vector<int64_t> aoff(iupac.size());
@@ -445,7 +522,32 @@ extern "C" int ntl_batch_pack(ntl_ctx *c, const char *const *seq, const int64_t 
     c->tm.packed_bytes = words * 4;
     c->tm.window_bytes = wins * 2 * c->dev.n_tracks;
     c->state = ST_PACKED;
+    if (overlap) {
+        /* the 4-bit arena (if any) and the tables follow; a grown device buffer means starting the copy over */
+        void *before = c->d_packed.p;
+        int rc1 = ensure_device_buffers(c, words);
+        if (rc1 != NTL_OK) return rc1;
+        if (c->d_packed.p != before) up_words = 0;
+        if (words > up_words)
+            CK(c, cudaMemcpyAsync((uint32_t *)c->d_packed.p + up_words, (uint32_t *)c->h_packed.p + up_words,
+                                  (size_t)(words - up_words) * 4, cudaMemcpyHostToDevice, c->stream));
+        if (c->meta_bytes > 0)
+            CK(c, cudaMemcpyAsync(c->d_meta.p, c->h_meta.p, c->meta_bytes, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaEventRecord(c->ev[1], c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        CK(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+        c->tm.h2d_ms = ms;                       /* first copy issued -> last copy done; overlaps pack_ms */
+        c->tm.h2d_bytes = words * 4 + (int64_t)c->meta_bytes;
+        c->tm.pack_ms = now_ms() - t0;
+        c->state = ST_UPLOADED;
+    }
     return NTL_OK;
+}
+
+extern "C" int ntl_batch_pack(ntl_ctx *c, const char *const *seq, const int64_t *len, int32_t n)
+{
+    return pack_internal(c, seq, len, n, false);
 }
 
 /* ============================================================================================== upload */
@@ -454,15 +556,7 @@ extern "C" int ntl_batch_upload(ntl_ctx *c)
     if (!c) return NTL_ERR_ARG;
     if (c->state < ST_PACKED) return fail(c, NTL_ERR_STATE, "ntl_batch_upload before ntl_batch_pack");
     CK(c, cudaSetDevice(c->device));
-    const int32_t n = c->n_reads;
-    const int T = c->dev.n_tracks;
-    CK(c, c->d_packed.ensure((size_t)c->total_words * 4 + 64));
-    CK(c, c->d_meta.ensure(c->meta_bytes + 16));
-    CK(c, c->d_results.ensure((size_t)n * sizeof(ntl_read_result) + 64));
-    CK(c, c->d_cum.ensure((size_t)c->total_windows * 2 * T + 64));
-    CK(c, c->d_pass.ensure((size_t)n + 64));
-    CK(c, c->d_flags.ensure((size_t)n * 4 + 64));         /* candidate list of the locate kernel */
-    if (c->dev.debug_stages) CK(c, c->d_stages.ensure((size_t)n * 3 * sizeof(ntl_stage) + 64));
+    { int rc0 = ensure_device_buffers(c, c->total_words); if (rc0 != NTL_OK) return rc0; }
     CK(c, cudaEventRecord(c->ev[0], c->stream));
     if (c->total_words > 0)
         CK(c, cudaMemcpyAsync(c->d_packed.p, c->h_packed.p, (size_t)c->total_words * 4, cudaMemcpyHostToDevice, c->stream));
@@ -620,8 +714,7 @@ extern "C" int ntl_scan_batch(ntl_ctx *c, const char *const *seq, const int64_t 
 {
     if (!c) return NTL_ERR_ARG;
     const double t0 = now_ms();
-    int rc = ntl_batch_pack(c, seq, len, n);
-    if (rc == NTL_OK) rc = ntl_batch_upload(c);
+    int rc = pack_internal(c, seq, len, n, /*overlap=*/true);
     if (rc == NTL_OK) rc = ntl_batch_run(c);
     if (rc == NTL_OK) rc = ntl_batch_download(c, results);
     c->tm.total_ms = now_ms() - t0;

@@ -82,17 +82,75 @@ static inline bool block_avx2(const char *s, int64_t L, int rc, int64_t b0, uint
     } else {
         v = _mm256_loadu_si256((const __m256i *)(s + b0));
     }
+    /* A/C/G/T in either case <=> (c | 0x20) equals the letter its low nibble selects: a=0x61 c=0x63 g=0x67 t=0x74 */
+    const __m256i lut = _mm256_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0,
+                                         0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0);
     const __m256i u = _mm256_or_si256(v, _mm256_set1_epi8(0x20));
-    __m256i ok = _mm256_cmpeq_epi8(u, _mm256_set1_epi8('a'));
-    ok = _mm256_or_si256(ok, _mm256_cmpeq_epi8(u, _mm256_set1_epi8('c')));
-    ok = _mm256_or_si256(ok, _mm256_cmpeq_epi8(u, _mm256_set1_epi8('g')));
-    ok = _mm256_or_si256(ok, _mm256_cmpeq_epi8(u, _mm256_set1_epi8('t')));
-    if (_mm256_movemask_epi8(ok) != -1) return false;
+    const __m256i want = _mm256_shuffle_epi8(lut, _mm256_and_si256(v, _mm256_set1_epi8(0x0f)));
+    if (_mm256_movemask_epi8(_mm256_cmpeq_epi8(u, want)) != -1) return false;
     uint32_t l = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));   /* ASCII bit 1 -> code bit 0 */
     uint32_t h = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));   /* ASCII bit 2 -> code bit 1 */
     if (rc) h = ~h;
     *lo = l; *hi = h;
     return true;
+}
+#endif
+
+#if defined(__x86_64__)
+/* 128 letters -> one 32-byte quad {lo[4], hi[4]} per iteration, branch-free inside: four loads (byte-reversed for
+ * --rc), ONE validity test (c | 0x20 must equal the letter its low nibble selects: a=0x61 c=0x63 g=0x67 t=0x74),
+ * eight movemasks (ASCII bit 1 -> lo plane, bit 2 -> hi plane; complement = ~hi), one 1-bit shift of the two
+ * 128-bit planes (the pad bit), one 32-byte store.  Returns the number of full quads written, or -1 if a letter is
+ * not A/C/G/T; the carries are the top bits that belong to bit 0 of the next word. */
+template <bool RC>
+__attribute__((target("avx2")))
+static int64_t pack_quads_avx2_t(const char *s, int64_t L, uint32_t *dst, uint32_t *carry_lo, uint32_t *carry_hi)
+{
+    const int64_t full = L >> 7;
+    const __m256i lut = _mm256_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0,
+                                         0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i rev = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0,
+                                         15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    const __m256i m0f = _mm256_set1_epi8(0x0f), c20 = _mm256_set1_epi8(0x20);
+    uint64_t cl = *carry_lo, ch = *carry_hi;
+    for (int64_t q = 0; q < full; q++) {
+        __m256i v[4];
+        if (!RC) {
+            const char *b = s + (q << 7);
+            for (int j = 0; j < 4; j++) v[j] = _mm256_loadu_si256((const __m256i *)(b + 32 * j));
+        } else {
+            const char *b = s + (L - ((q + 1) << 7));
+            for (int j = 0; j < 4; j++) {
+                __m256i x = _mm256_loadu_si256((const __m256i *)(b + 32 * (3 - j)));
+                x = _mm256_shuffle_epi8(x, rev);
+                v[j] = _mm256_permute2x128_si256(x, x, 0x01);
+            }
+        }
+        __m256i ok = _mm256_set1_epi8(-1);
+        for (int j = 0; j < 4; j++)
+            ok = _mm256_and_si256(ok, _mm256_cmpeq_epi8(_mm256_or_si256(v[j], c20),
+                                                        _mm256_shuffle_epi8(lut, _mm256_and_si256(v[j], m0f))));
+        if (_mm256_movemask_epi8(ok) != -1) return -1;
+        uint64_t l[4], h[4];
+        for (int j = 0; j < 4; j++) {
+            l[j] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v[j], 6));
+            h[j] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v[j], 5));
+        }
+        uint64_t la = l[0] | (l[1] << 32), lb = l[2] | (l[3] << 32);
+        uint64_t ha = h[0] | (h[1] << 32), hb = h[2] | (h[3] << 32);
+        if (RC) { ha = ~ha; hb = ~hb; }
+        uint64_t out[4];
+        out[0] = (la << 1) | cl; out[1] = (lb << 1) | (la >> 63);
+        out[2] = (ha << 1) | ch; out[3] = (hb << 1) | (ha >> 63);
+        cl = lb >> 63; ch = hb >> 63;
+        memcpy(dst + q * 8, out, 32);
+    }
+    *carry_lo = (uint32_t)cl; *carry_hi = (uint32_t)ch;
+    return full;
+}
+static int64_t pack_quads_avx2(const char *s, int64_t L, int rc, uint32_t *dst, uint32_t *carry_lo, uint32_t *carry_hi)
+{
+    return rc ? pack_quads_avx2_t<true>(s, L, dst, carry_lo, carry_hi) : pack_quads_avx2_t<false>(s, L, dst, carry_lo, carry_hi);
 }
 #endif
 
@@ -116,6 +174,13 @@ int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst)
     const int64_t n_blocks = (L + 31) >> 5;          /* unshifted 32-letter blocks */
     uint32_t carry_lo = 0, carry_hi = 0;             /* bit 31 of the previous block -> bit 0 of the next word */
     int64_t k = 0;
+#if defined(__x86_64__)
+    if (g_have_avx2) {
+        const int64_t full = pack_quads_avx2(s, L, rc, dst, &carry_lo, &carry_hi);
+        if (full < 0) return 1;
+        k = full << 2;
+    }
+#endif
     for (; k < n_blocks; k++) {
         uint32_t lo, hi;
         const int64_t b0 = k << 5;

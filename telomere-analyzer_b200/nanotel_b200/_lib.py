@@ -56,7 +56,7 @@ assert RESULT_DTYPE.itemsize == 64
 EXPORTS = [
     "ntl_version", "ntl_create", "ntl_destroy", "ntl_last_error", "ntl_scan_batch", "ntl_scan_batch_concat",
     "ntl_batch_pack", "ntl_batch_upload", "ntl_batch_run", "ntl_batch_enqueue", "ntl_batch_wait", "ntl_batch_download", "ntl_get_timings", "ntl_stream",
-    "ntl_get_windows", "ntl_get_stages", "ntl_jit_compile_check", "ntl_assign_serials", "ntl_count_windows",
+    "ntl_get_windows", "ntl_get_stages", "ntl_jit_compile_check", "ntl_pack_read", "ntl_assign_serials", "ntl_count_windows",
 ]
 
 _lib = None
@@ -94,6 +94,8 @@ def load() -> C.CDLL:
     L.ntl_get_stages.argtypes = [vp, i32, i32, C.POINTER(Stage)]
     L.ntl_jit_compile_check.argtypes = [C.POINTER(Params), C.c_char_p, C.c_char_p, C.c_int, C.c_char_p]
     L.ntl_jit_compile_check.restype = C.c_long
+    L.ntl_pack_read.argtypes = [C.c_char_p, i64, i32, vp, i64, C.POINTER(i32)]
+    L.ntl_pack_read.restype = C.c_long
     L.ntl_assign_serials.argtypes = [vp, i32, i32, vp, vp, C.POINTER(i32)]
     L.ntl_count_windows.argtypes = [i64, i32]
     L.ntl_count_windows.restype = i32

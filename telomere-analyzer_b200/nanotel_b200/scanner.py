@@ -84,7 +84,8 @@ class Scanner:
         if n == 0:
             return np.zeros(0, _lib.RESULT_DTYPE)
         buf = (C.c_char * (n * 64)).from_address(ptr.value)
-        return np.frombuffer(buf, dtype=_lib.RESULT_DTYPE, count=n)
+        # one flat memcpy out of the context's pinned buffer (a structured-dtype .copy() is ~10x slower)
+        return np.frombuffer(buf, dtype=np.uint8, count=n * 64).copy().view(_lib.RESULT_DTYPE)
 
     def scan(self, seqs: Sequence[bytes]) -> np.ndarray:
         """ntl_scan_batch: host ASCII reads in, one RESULT_DTYPE record per read out (a copy)."""
@@ -93,7 +94,7 @@ class Scanner:
         out = C.c_void_p()
         self._check(self._L.ntl_scan_batch(self._h, arr, lens.ctypes.data, len(seqs), C.byref(out)))
         self._n = len(seqs)
-        return self._results_view(out, self._n).copy()
+        return self._results_view(out, self._n)
 
     @staticmethod
     def _marshal_concat(buf: np.ndarray, offsets: np.ndarray):
@@ -110,7 +111,7 @@ class Scanner:
         out = C.c_void_p()
         self._check(self._L.ntl_scan_batch(self._h, ptrs.ctypes.data, lens.ctypes.data, len(lens), C.byref(out)))
         self._n = len(lens)
-        return self._results_view(out, self._n).copy()
+        return self._results_view(out, self._n)
 
     def pack_concat(self, buf: np.ndarray, offsets: np.ndarray) -> None:
         buf, ptrs, lens = self._marshal_concat(buf, offsets)
@@ -139,7 +140,7 @@ class Scanner:
     def download(self) -> np.ndarray:
         out = C.c_void_p()
         self._check(self._L.ntl_batch_download(self._h, C.byref(out)))
-        return self._results_view(out, self._n).copy()
+        return self._results_view(out, self._n)
 
     def timings(self) -> dict:
         t = _lib.Timings()

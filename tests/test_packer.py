@@ -1,0 +1,76 @@
+"""CPU: the host packer (AVX2 + scalar tails, --rc folded in, 4-bit fallback) against a plain numpy restatement of
+the layout in csrc/ntl_dev.h: position p (1-based, after rc) is bit p of the read's stream; quads of 128 positions are
+{lo[4], hi[4]} with code (ASCII >> 1) & 3, or {A[4], C[4], G[4], T[4]} for reads with IUPAC letters."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+NIB = {c: v for c, v in zip(b"ACGTMRWSYKVHDBN", [1, 2, 4, 8, 3, 5, 9, 6, 10, 12, 7, 11, 13, 14, 15])}
+NIB.update({ord("-"): 0, ord("+"): 0, ord("."): 0})
+
+
+def _pack(seq: bytes, rc: bool):
+    from nanotel_b200 import _lib
+    L = _lib.load()
+    cap = ((len(seq) >> 5) + 8) * 4 * 4
+    w = np.zeros(cap, np.uint32)
+    fb = C.c_int32()
+    n = L.ntl_pack_read(seq, len(seq), int(rc), w.ctypes.data, cap, C.byref(fb))
+    assert n > 0, n
+    return w[:n], bool(fb.value)
+
+
+def _expected(seq: bytes, rc: bool):
+    from oracle import oracle as O
+    s = O.revcomp(seq) if rc else seq.upper()
+    n_words = (len(s) >> 5) + 1
+    n_quads = (n_words + 3) // 4
+    acgt = all(c in b"ACGT" for c in s)
+    planes = 2 if acgt else 4
+    bits = np.zeros((planes, n_quads * 128), np.uint8)
+    for p, c in enumerate(s, 1):
+        if acgt:
+            code = (c >> 1) & 3
+            bits[0, p] = code & 1
+            bits[1, p] = code >> 1
+        else:
+            nb = NIB[c]
+            for k in range(4):
+                bits[k, p] = (nb >> k) & 1
+    words = np.zeros(n_quads * 4 * planes, np.uint32)
+    for k in range(planes):
+        w = np.packbits(bits[k].reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).ravel()
+        for q in range(n_quads):
+            words[q * 4 * planes + 4 * k: q * 4 * planes + 4 * k + 4] = w[4 * q: 4 * q + 4]
+    return words, not acgt
+
+
+@pytest.mark.parametrize("rc", [False, True])
+def test_packer_matches_layout(rc):
+    rng = np.random.default_rng(12)
+    lens = list(range(1, 70)) + [95, 96, 97, 127, 128, 129, 255, 256, 257, 383, 384, 385, 1000, 4095, 4096, 4097, 10007]
+    for L in lens:
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTacgt", np.uint8), L))
+        got, fb = _pack(seq, rc)
+        exp, efb = _expected(seq, rc)
+        assert not fb and not efb
+        assert np.array_equal(got, exp), (L, rc)
+    for L in (1, 5, 33, 128, 129, 700):
+        seq = bytearray(rng.choice(np.frombuffer(b"ACGT", np.uint8), L))
+        seq[int(rng.integers(0, L))] = ord("N")
+        if L > 40:
+            seq[37] = ord("r")
+            seq[L - 1] = ord("-")
+        got, fb = _pack(bytes(seq), rc)
+        exp, efb = _expected(bytes(seq), rc)
+        assert fb and efb and np.array_equal(got, exp), (L, rc)
+
+
+def test_packer_rejects_non_dna():
+    from nanotel_b200 import _lib
+    L = _lib.load()
+    w = np.zeros(64, np.uint32)
+    fb = C.c_int32()
+    assert L.ntl_pack_read(b"ACGTXACGT", 9, 0, w.ctypes.data, 64, C.byref(fb)) == -3
+    assert L.ntl_pack_read(b"ACGT", 0, 0, w.ctypes.data, 64, C.byref(fb)) == -1

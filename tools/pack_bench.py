@@ -1,0 +1,21 @@
+"""Host packer throughput vs thread count (ntl_batch_pack only; no kernels)."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "telomere-analyzer_b200"))
+from nanotel_b200 import Scanner  # noqa: E402
+from nanotel_b200.synth import synth_reads  # noqa: E402
+
+buf, off, meta = synth_reads(int(sys.argv[1]) if len(sys.argv) > 1 else 100000, 20261020)
+for nt in (1, 2, 4, 8, 16, 32):
+    sc = Scanner("YYAGGG", rc=True, host_threads=nt)
+    best = 1e9
+    for _ in range(4):
+        t0 = time.perf_counter()
+        sc.pack_concat(buf, off)
+        best = min(best, time.perf_counter() - t0)
+    tm = sc.timings()
+    print("threads %2d  wall %.1f ms  pack_ms %.1f  -> %.1f GB/s ASCII" % (nt, best * 1e3, tm["pack_ms"], meta["bases"] / best / 1e9))
+    sc.close()
