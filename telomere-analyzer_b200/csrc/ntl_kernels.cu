@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) ntl_scan_kernel(const ntl_scan_args a)
  * Shared by K3 and K4: random access into a packed read
  * ============================================================================================================= */
 #define NTL_NONE (-999999999)
-#define NTL_TRIAGE_MAX_WIN 384
+#define NTL_TRIAGE_MAX_WIN 1024
 #define NTL_IMAX 2147483647
 
 struct ReadView {
@@ -263,7 +263,8 @@ struct WinTab {                 /* the window table of one track (analyze_subtel
     const uint16_t *cum;
     int n, S, L;
     int thr_reg, thr_last;      /* smallest telomeric count of a regular window / of this read's last window */
-    bool any;                   /* K2 saw at least one telomeric window on this track                         */
+    bool any;                   /* at least one telomeric window on this track                                */
+    const u32 *bits;            /* class bits of all windows (1 = telomeric) in shared memory, or NULL        */
 };
 __device__ __forceinline__ int wt_start(const WinTab &w, int k) { return 1 + k * w.S; }
 __device__ __forceinline__ int wt_end(const WinTab &w, int k) { return k == w.n - 1 ? w.L : (k + 1) * w.S; }
@@ -278,7 +279,12 @@ __device__ __forceinline__ bool wt_telo_count(const WinTab &w, int k, int count)
 {
     return count >= (k == w.n - 1 ? w.thr_last : w.thr_reg);
 }
-__device__ __forceinline__ bool wt_telo(const WinTab &w, int k) { return w.any && wt_telo_count(w, k, wt_count(w, k)); }
+__device__ __forceinline__ bool wt_telo(const WinTab &w, int k)
+{
+    if (!w.any) return false;
+    if (w.bits != nullptr) return (w.bits[k >> 5] >> (k & 31)) & 1u;
+    return wt_telo_count(w, k, wt_count(w, k));
+}
 
 /* The run/score machine of find_telo_position (NanoTel.R:1003-1025 forward, :1046-1068 backward) over windows
  * i0, i0+dir, ..., i1 (0-based, inclusive).  Returns the window index at which  in_a_row >= R && score >= T  first
@@ -288,6 +294,36 @@ __device__ __noinline__ int run_scan(const WinTab &w, int i0, int i1, int dir, d
     double score = 0.0;
     int run_first = -1, in_a_row = 0;
     const int total = (i1 - i0) * dir + 1;
+    if (w.bits != nullptr) {
+        /* class bits are in shared memory: walk them word by word, skipping runs of non-telomeric windows with
+         * ffs / clz; only the windows that enter a score are read back (warp-uniform) */
+        int cur = i0;
+        while (dir > 0 ? cur <= i1 : cur >= i1) {
+            const u32 word = w.bits[cur >> 5];
+            int z;
+            if (dir > 0) {
+                const u32 m = word >> (cur & 31);
+                if (m == 0u) { score = 0.0; run_first = -1; in_a_row = 0; cur = ((cur >> 5) + 1) << 5; continue; }
+                z = __ffs((int)m) - 1;
+            } else {
+                const u32 m = word << (31 - (cur & 31));
+                if (m == 0u) { score = 0.0; run_first = -1; in_a_row = 0; cur = ((cur >> 5) << 5) - 1; continue; }
+                z = __clz((int)m);
+            }
+            if (z > 0) {
+                score = 0.0; run_first = -1; in_a_row = 0;
+                cur += dir * z;
+                if (dir > 0 ? cur > i1 : cur < i1) break;
+            }
+            in_a_row += 1;
+            score = score + (double)wt_count(w, cur) / (double)(wt_end(w, cur) - wt_start(w, cur) + 1);   /* :1014 */
+            if (run_first == -1) run_first = cur;
+            if ((double)in_a_row >= R && score >= T) { *first = run_first; return cur; }
+            cur += dir;
+        }
+        *first = run_first;
+        return -1;
+    }
     /* 128 windows per step: four independent loads per lane are in flight before the first ballot */
     for (int done = 0; done < total; done += 128) {
         int cnt[4];
@@ -604,6 +640,10 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
         const int L = a.len[r];
         const int n_win = ntl_nwin(L, S);
         const long long wo = a.win_off[r];
+        /* first word of the read (positions 0..31 hold s[1..18]); issued now so that its DRAM latency overlaps
+         * the window loop.  For a 4-bit read word 4 is another plane: read but not used. */
+        const u32 *q0 = a.packed + a.woff[r];
+        const u32 lo0 = __ldg(q0), hi0 = __ldg(q0 + 4);
         int status = 0;
         bool simple = true;
         if (a.pass != nullptr && a.pass[r] == 0) status = NTL_READ_FILTERED;
@@ -619,35 +659,49 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
                 const int thr_reg = c_prm.thr_reg;
                 const int thr_last = (int)a.thr[L - (n_win - 1) * S];
                 bool tel = false;
-                for (int t = 0; t < T; t++) {
-                    const uint16_t *cm = a.cum[t] + wo;
-                    const uint4 *cv = reinterpret_cast<const uint4 *>(cm);
-                    const int n_reg = n_win - 1;                 /* windows 0 .. n_win-2 have width S */
-                    const int full = n_reg >> 3;
-                    u32 prev = 0u;
-#pragma unroll 4
-                    for (int g = 0; g < full; g++) {
-                        const uint4 v = __ldg(cv + g);
-                        const u32 x[4] = {v.x, v.y, v.z, v.w};
+                const int n_reg = n_win - 1;                     /* windows 0 .. n_win-2 have width S */
+                const int full = n_reg >> 3;
+                u32 prev[3] = {0u, 0u, 0u};
+                /* 4 groups x T tracks = up to 12 independent 16-byte loads in flight per thread */
+                for (int g = 0; g < full; g += 4) {
+                    uint4 v[3][4];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const u32 l16 = x[q] & 0xffffu, h16 = x[q] >> 16;
-                            tel |= (int)((l16 - prev) & 0xffffu) >= thr_reg;
-                            tel |= (int)((h16 - l16) & 0xffffu) >= thr_reg;
-                            prev = h16;
+                    for (int t = 0; t < 3; t++)
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (t < T && g + u < full)
+                                v[t][u] = __ldg(reinterpret_cast<const uint4 *>(a.cum[t] + wo) + g + u);
+#pragma unroll
+                    for (int t = 0; t < 3; t++)
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (t < T && g + u < full) {
+                                const u32 x[4] = {v[t][u].x, v[t][u].y, v[t][u].z, v[t][u].w};
+#pragma unroll
+                                for (int q = 0; q < 4; q++) {
+                                    const u32 l16 = x[q] & 0xffffu, h16 = x[q] >> 16;
+                                    tel |= (int)((l16 - prev[t]) & 0xffffu) >= thr_reg;
+                                    tel |= (int)((h16 - l16) & 0xffffu) >= thr_reg;
+                                    prev[t] = h16;
+                                }
+                            }
+                }
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    if (t < T) {
+                        const uint16_t *cm = a.cum[t] + wo;
+                        u32 pv = prev[t];
+                        for (int k = full << 3; k < n_win; k++) {
+                            const u32 cur = cm[k];
+                            tel |= (int)((cur - pv) & 0xffffu) >= (k == n_win - 1 ? thr_last : thr_reg);
+                            pv = cur;
                         }
-                    }
-                    for (int k = full << 3; k < n_win; k++) {
-                        const u32 cur = cm[k];
-                        tel |= (int)((cur - prev) & 0xffffu) >= (k == n_win - 1 ? thr_last : thr_reg);
-                        prev = cur;
                     }
                 }
                 simple = !tel;
             }
             if (simple) {
-                const u32 *q = a.packed + a.woff[r];
-                simple = !triage_first_window_hit(q[0], q[4], T);
+                simple = !triage_first_window_hit(lo0, hi0, T);
             }
             if (!simple) cand = true;
         }
@@ -683,10 +737,13 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
 /* =============================================================================================================
  * K3b: full locator, one WARP per candidate read (persistent grid, dynamic work counter)
  * ============================================================================================================= */
-__device__ void locate_read(const ntl_read_args &a, int r, int lane);
+#define NTL_BITS_WORDS 512          /* class bits of up to 16384 windows per warp in shared memory */
+
+__device__ void locate_read(const ntl_read_args &a, int r, int lane, u32 *sbits);
 
 __global__ void __launch_bounds__(128) ntl_locate_kernel(const ntl_read_args a)
 {
+    __shared__ u32 s_bits[4][NTL_BITS_WORDS];
     const int lane = threadIdx.x & 31;
     const int n_cand = (int)a.counters[0];
     for (;;) {
@@ -694,34 +751,48 @@ __global__ void __launch_bounds__(128) ntl_locate_kernel(const ntl_read_args a)
         if (lane == 0) i = (int)atomicAdd(&a.counters[1], 1u);
         i = __shfl_sync(NTL_FULL, i, 0);
         if (i >= n_cand) break;
-        locate_read(a, a.cand[i], lane);
+        locate_read(a, a.cand[i], lane, s_bits[threadIdx.x >> 5]);
     }
 }
 
 /* any window of this track with  !(count / width < min_density)?  256 prefixes per warp-wide 16-byte load, all
  * loads independent (the window range of a read starts on a multiple of 8 entries and is padded to one) */
-__device__ __noinline__ bool warp_any_telomeric(const WinTab &w, int lane)
+__device__ __noinline__ bool warp_any_telomeric(const WinTab &w, int lane, u32 *bits)
 {
+    /* also leaves the class bits (1 = telomeric window) in bits[] (shared memory, one warp) when it is given:
+     * lane l of a step holds windows 8 l' .. 8 l' + 7, four lanes make one 32-bit word */
     const uint4 *cv = reinterpret_cast<const uint4 *>(w.cum);
     const int groups = (w.n + 7) >> 3;
     bool tel = false;
-    for (int g = lane; g < groups; g += 32) {
-        const uint4 v = __ldg(cv + g);
-        const u32 x[4] = {v.x, v.y, v.z, v.w};
-        u32 prev = g > 0 ? (u32)w.cum[8 * g - 1] : 0u;
+    for (int g0 = 0; g0 < groups; g0 += 32) {
+        const int g = g0 + lane;
+        u32 b8 = 0u;
+        if (g < groups) {
+            const uint4 v = __ldg(cv + g);
+            const u32 x[4] = {v.x, v.y, v.z, v.w};
+            u32 prev = g > 0 ? (u32)w.cum[8 * g - 1] : 0u;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int k = 8 * g + 2 * q;
-            const u32 l16 = x[q] & 0xffffu, h16 = x[q] >> 16;
-            if (k < w.n) tel |= wt_telo_count(w, k, (int)((l16 - prev) & 0xffffu));
-            if (k + 1 < w.n) tel |= wt_telo_count(w, k + 1, (int)((h16 - l16) & 0xffffu));
-            prev = h16;
+            for (int q = 0; q < 4; q++) {
+                const int k = 8 * g + 2 * q;
+                const u32 l16 = x[q] & 0xffffu, h16 = x[q] >> 16;
+                if (k < w.n && wt_telo_count(w, k, (int)((l16 - prev) & 0xffffu))) b8 |= 1u << (2 * q);
+                if (k + 1 < w.n && wt_telo_count(w, k + 1, (int)((h16 - l16) & 0xffffu))) b8 |= 2u << (2 * q);
+                prev = h16;
+            }
+        }
+        tel |= b8 != 0u;
+        if (bits != nullptr) {
+            u32 wd = b8 << (8 * (lane & 3));
+            wd |= __shfl_xor_sync(NTL_FULL, wd, 1);
+            wd |= __shfl_xor_sync(NTL_FULL, wd, 2);
+            if ((lane & 3) == 0 && g < groups) bits[g >> 2] = wd;
         }
     }
+    __syncwarp();
     return __any_sync(NTL_FULL, tel);
 }
 
-__device__ void locate_read(const ntl_read_args &a, int r, int lane)
+__device__ void locate_read(const ntl_read_args &a, int r, int lane, u32 *sbits)
 {
     ntl_read_result *res = reinterpret_cast<ntl_read_result *>(a.results) + r;
     ntl_stage *stg = a.stages ? reinterpret_cast<ntl_stage *>(a.stages) + (size_t)r * 3 : nullptr;
@@ -746,7 +817,11 @@ __device__ void locate_read(const ntl_read_args &a, int r, int lane)
             w.cum = a.cum[t] + a.win_off[r]; w.n = n_win > 0 ? n_win : 0; w.S = S; w.L = rv.L;
             w.thr_reg = c_prm.thr_reg;
             w.thr_last = w.n > 0 ? (int)a.thr[wt_end(w, w.n - 1) - wt_start(w, w.n - 1) + 1] : 0;
-            w.any = w.n > 0 && warp_any_telomeric(w, lane);
+            w.bits = nullptr;
+            __syncwarp();                                           /* the previous track is done with sbits */
+            u32 *bits = w.n <= NTL_BITS_WORDS * 32 ? sbits : nullptr;
+            w.any = w.n > 0 && warp_any_telomeric(w, lane, bits);
+            w.bits = bits;
             const int k = t >= 1 ? 1 : 0;
             const bool use_tvr = t == 2;
 
