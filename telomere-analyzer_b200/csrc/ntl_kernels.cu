@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) ntl_scan_kernel(const ntl_scan_args a)
  * Shared by K3 and K4: random access into a packed read
  * ============================================================================================================= */
 #define NTL_NONE (-999999999)
-#define NTL_TRIAGE_MAX_WIN 1024
+#define NTL_TRIAGE_MAX_WIN 8192
 #define NTL_IMAX 2147483647
 
 struct ReadView {
@@ -627,15 +627,19 @@ __device__ __forceinline__ bool triage_first_window_hit(u32 lo, u32 hi, int T)
     return any;
 }
 
+/* Eight lanes per read ("team"), four reads per warp: the team walks the read's window prefixes eight 16-byte
+ * groups at a time (128 contiguous bytes per track and step), so the longest read costs n_win / 64 dependent steps
+ * instead of n_win / 8, and the loads of a team coalesce. */
 __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    const int sub = lane & 7;
+    const u32 tmask = 0xffu << (lane & 24);
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     bool cand = false;
     int r = -1;
-    if (i < a.n_reads) {
-        r = a.order[i];
-        ntl_read_result *res = reinterpret_cast<ntl_read_result *>(a.results) + r;
+    if (slot < a.n_reads) {
+        r = a.order[slot];
         const int S = c_prm.S, T = c_prm.n_tracks;
         const int L = a.len[r];
         const int n_win = ntl_nwin(L, S);
@@ -648,64 +652,65 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
         bool simple = true;
         if (a.pass != nullptr && a.pass[r] == 0) status = NTL_READ_FILTERED;
         else {
-            /* long reads go to the warp-per-read kernel: one thread walking thousands of windows would be the
-             * tail of this launch */
             simple = a.fmt[r] == 0 && n_win >= 1 && n_win <= NTL_TRIAGE_MAX_WIN;
             if (simple)
                 simple = c_prm.right_edge ? ((n_win >= 2 ? S : L) < L - 200) : (1 + (n_win - 1) * S > 200);
             if (simple) {
-                /* any window with  !(count / width < min_density)  on any track?  (8 prefixes per 16-byte load;
-                 * every read's window range starts on a multiple of 8 entries) */
+                /* any window with  !(count / width < min_density)  on any track?  Every read's window range starts
+                 * on a multiple of 8 entries, so groups of 8 prefixes are 16-byte aligned. */
                 const int thr_reg = c_prm.thr_reg;
                 const int thr_last = (int)a.thr[L - (n_win - 1) * S];
                 bool tel = false;
-                const int n_reg = n_win - 1;                     /* windows 0 .. n_win-2 have width S */
-                const int full = n_reg >> 3;
-                u32 prev[3] = {0u, 0u, 0u};
-                /* 4 groups x T tracks = up to 12 independent 16-byte loads in flight per thread */
-                for (int g = 0; g < full; g += 4) {
-                    uint4 v[3][4];
+                const int full = (n_win - 1) >> 3;               /* groups made of width-S windows only */
+                u32 carry[3] = {0u, 0u, 0u};                     /* last prefix of the previous step */
+                for (int g0 = 0; g0 < full; g0 += 8) {
+                    const int g = g0 + sub;
+                    uint4 v[3];
 #pragma unroll
                     for (int t = 0; t < 3; t++)
+                        v[t] = (t < T && g < full) ? __ldg(reinterpret_cast<const uint4 *>(a.cum[t] + wo) + g)
+                                                   : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            if (t < T && g + u < full)
-                                v[t][u] = __ldg(reinterpret_cast<const uint4 *>(a.cum[t] + wo) + g + u);
-#pragma unroll
-                    for (int t = 0; t < 3; t++)
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            if (t < T && g + u < full) {
-                                const u32 x[4] = {v[t][u].x, v[t][u].y, v[t][u].z, v[t][u].w};
+                    for (int t = 0; t < 3; t++) {
+                        if (t < T) {
+                            const u32 last = v[t].w >> 16;
+                            u32 prev = __shfl_up_sync(tmask, last, 1, 8);
+                            if (sub == 0) prev = carry[t];
+                            carry[t] = __shfl_sync(tmask, last, 7, 8);
+                            if (g < full) {
+                                const u32 x[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
 #pragma unroll
                                 for (int q = 0; q < 4; q++) {
                                     const u32 l16 = x[q] & 0xffffu, h16 = x[q] >> 16;
-                                    tel |= (int)((l16 - prev[t]) & 0xffffu) >= thr_reg;
+                                    tel |= (int)((l16 - prev) & 0xffffu) >= thr_reg;
                                     tel |= (int)((h16 - l16) & 0xffffu) >= thr_reg;
-                                    prev[t] = h16;
+                                    prev = h16;
                                 }
                             }
-                }
-#pragma unroll
-                for (int t = 0; t < 3; t++) {
-                    if (t < T) {
-                        const uint16_t *cm = a.cum[t] + wo;
-                        u32 pv = prev[t];
-                        for (int k = full << 3; k < n_win; k++) {
-                            const u32 cur = cm[k];
-                            tel |= (int)((cur - pv) & 0xffffu) >= (k == n_win - 1 ? thr_last : thr_reg);
-                            pv = cur;
                         }
                     }
                 }
-                simple = !tel;
+                /* the remaining <= 8 windows (the last one has its own width and threshold), one per lane */
+                {
+                    const int k = (full << 3) + sub;
+                    if (k < n_win) {
+#pragma unroll
+                        for (int t = 0; t < 3; t++) {
+                            if (t < T) {
+                                const uint16_t *cm = a.cum[t] + wo;
+                                const u32 cur = cm[k], pv = k > 0 ? (u32)cm[k - 1] : 0u;
+                                tel |= (int)((cur - pv) & 0xffffu) >= (k == n_win - 1 ? thr_last : thr_reg);
+                            }
+                        }
+                    }
+                }
+                simple = (__ballot_sync(tmask, tel) & tmask) == 0u;
             }
-            if (simple) {
-                simple = !triage_first_window_hit(lo0, hi0, T);
-            }
+            if (simple) simple = !triage_first_window_hit(lo0, hi0, T);
             if (!simple) cand = true;
         }
         if (!cand) {
+            /* the 64-byte record goes out as four 16-byte stores from lanes 0..3 of the team */
             ntl_read_result o;
             o.status = status;
             o.n_win = n_win > 0 ? n_win : 0;
@@ -714,23 +719,25 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
                 o.track[t].start = live ? -1 : 0; o.track[t].end = 0; o.track[t].density = 0.0;
             }
             o.win_offset = wo;
-            *res = o;
-            if (a.stages != nullptr && status == 0) {
+            if (sub < 4)
+                reinterpret_cast<uint4 *>(reinterpret_cast<ntl_read_result *>(a.results) + r)[sub] =
+                    reinterpret_cast<const uint4 *>(&o)[sub];
+            if (a.stages != nullptr && status == 0 && sub < T) {
                 ntl_stage s;
                 s.coarse_start = s.coarse_end = s.acc_start = s.acc_end = s.edge_start = s.edge_end = -1;
                 s.acc_density = 0.0;
-                for (int t = 0; t < T; t++) reinterpret_cast<ntl_stage *>(a.stages)[(size_t)r * 3 + t] = s;
+                reinterpret_cast<ntl_stage *>(a.stages)[(size_t)r * 3 + sub] = s;
             }
         }
     }
-    /* warp-aggregated append to the candidate list */
-    const u32 cm = __ballot_sync(NTL_FULL, cand);
+    /* warp-aggregated append to the candidate list (one entry per team) */
+    const u32 cm = __ballot_sync(NTL_FULL, cand && sub == 0);
     if (cm) {
         int base = 0;
         const int leader = __ffs((int)cm) - 1;
         if (lane == leader) base = (int)atomicAdd(&a.counters[0], (u32)__popc(cm));
         base = __shfl_sync(NTL_FULL, base, leader);
-        if (cand) a.cand[base + __popc(cm & ((1u << lane) - 1u))] = r;
+        if (cand && sub == 0) a.cand[base + __popc(cm & ((1u << lane) - 1u))] = r;
     }
 }
 
@@ -908,7 +915,7 @@ extern "C" cudaError_t ntl_k_filter(const ntl_read_args *a, cudaStream_t st)
 extern "C" cudaError_t ntl_k_triage(const ntl_read_args *a, cudaStream_t st)
 {
     if (a->n_reads <= 0) return cudaSuccess;
-    ntl_triage_kernel<<<(a->n_reads + 255) / 256, 256, 0, st>>>(*a);
+    ntl_triage_kernel<<<(a->n_reads * 8 + 255) / 256, 256, 0, st>>>(*a);     /* 8 lanes per read */
     return cudaGetLastError();
 }
 
