@@ -88,6 +88,7 @@ struct ntl_ctx {
     int state = ST_EMPTY;
     int32_t n_reads = 0, n2 = 0, n4 = 0;
     int64_t total_words = 0, total_windows = 0, bases = 0;
+    size_t dens_offset = 0;
     size_t meta_bytes = 0, off_len = 0, off_woff = 0, off_winoff = 0, off_order = 0, off_fmt = 0;
 
     PinnedBuf h_packed, h_meta, h_results, h_cum, h_stages;
@@ -161,8 +162,10 @@ int digest_patterns(ntl_ctx *c, const std::vector<std::string> &in, ntl_dev_pat 
                 bool acc = d.fixed ? (d.nib[j] == base_nib[code]) : ((d.nib[j] & base_nib[code]) != 0);
                 d.mux2[j][code] = acc ? 0xffffffffu : 0u;
             }
-            for (int b = 0; b < 4; b++)
+            for (int b = 0; b < 4; b++) {
+                d.mux4[j][b] = (d.nib[j] & (1 << b)) ? 0xffffffffu : 0u;
                 if (d.nib[j] & (1 << b)) d.q4[b] |= 1u << j;
+            }
         }
         if (i == 0 || uniq[i - 1].size() != s.size()) group_begin[(*n_groups)++] = (int32_t)i;
     }
@@ -268,9 +271,16 @@ extern "C" int ntl_create(ntl_ctx **out, const ntl_params *p)
             while (cnt <= w && ((double)cnt / (double)w < p->min_density)) cnt++;
             thr[w] = (uint16_t)(cnt > 65535 ? 65535 : cnt);
         }
-        e = c->d_thr.ensure(thr.size() * 2);
+        /* dens[c] = (double)c / (double)S, the density of a width-S window holding c covered bases (:467) */
+        std::vector<double> dens((size_t)S + 1);
+        for (int32_t cc = 0; cc <= S; cc++) dens[cc] = (double)cc / (double)S;
+        const size_t thr_bytes = (thr.size() * 2 + 15) & ~(size_t)15;
+        e = c->d_thr.ensure(thr_bytes + dens.size() * 8);
         if (e == cudaSuccess)
             e = cudaMemcpy(c->d_thr.p, thr.data(), thr.size() * 2, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess)
+            e = cudaMemcpy((char *)c->d_thr.p + thr_bytes, dens.data(), dens.size() * 8, cudaMemcpyHostToDevice);
+        c->dens_offset = thr_bytes;
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
@@ -360,7 +370,7 @@ static int ensure_device_buffers(ntl_ctx *c, int64_t packed_words)
     CK(c, c->d_results.ensure((size_t)n * sizeof(ntl_read_result) + 64));
     CK(c, c->d_cum.ensure((size_t)c->total_windows * 2 * T + 64));
     CK(c, c->d_pass.ensure((size_t)n + 64));
-    CK(c, c->d_flags.ensure((size_t)n * 4 + 64));         /* candidate list of the locate kernel */
+    CK(c, c->d_flags.ensure((size_t)n * 20 + 128));       /* candidate list + per-candidate join state of the locate kernel */
     if (c->dev.debug_stages) CK(c, c->d_stages.ensure((size_t)n * 3 * sizeof(ntl_stage) + 64));
     return NTL_OK;
 }
@@ -599,8 +609,10 @@ extern "C" int ntl_batch_enqueue(ntl_ctx *c)
     for (int t = 0; t < 3; t++) ra.cum[t] = t < T ? (const uint16_t *)c->d_cum.p + (size_t)t * c->total_windows : nullptr;
     ra.results = c->d_results.p;
     ra.thr = (const uint16_t *)c->d_thr.p;
+    ra.dens = (const double *)((const char *)c->d_thr.p + c->dens_offset);
     ra.order = (const int32_t *)(dm + c->off_order);
     ra.cand = (int32_t *)c->d_flags.p;
+    ra.cand_state = (int32_t *)c->d_flags.p + (((size_t)n + 3) & ~(size_t)3);
     ra.counters = (uint32_t *)c->d_counter.p + 4;
     ra.stages = c->dev.debug_stages ? c->d_stages.p : nullptr;
     ra.n_reads = n;

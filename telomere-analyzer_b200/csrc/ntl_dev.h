@@ -33,6 +33,7 @@ typedef struct {
     int32_t  fixed;                    /* !grepl("[WSMKRYBDHVN]") (NanoTel.R:334): 1 = byte equality              */
     uint32_t mux2[NTL_DEV_MAX_LEN][4]; /* main scan, 2-bit reads: all-ones/zero word per 2-bit code c: letter j
                                           accepts code c under this pattern's own fixed flag                       */
+    uint32_t mux4[NTL_DEV_MAX_LEN][4]; /* all-ones/zero word per nibble bit A, C, G, T of letter j                */
     uint32_t q4[4];                    /* bit j set <=> pattern letter j has the A / C / G / T bit (nibble planes) */
     uint8_t  nib[NTL_DEV_MAX_LEN];     /* Biostrings nibble of letter j                                           */
     uint8_t  pad[2];
@@ -83,8 +84,10 @@ typedef struct {
     const uint16_t *cum[3];
     const uint16_t *thr;               /* [2 S + 2] smallest covered count that makes a window of that width
                                           telomeric: !(count / width < min_density), NanoTel.R:751-758         */
+    const double   *dens;              /* [S + 1] dens[c] = (double)c / (double)S (NanoTel.R:467 for width-S windows) */
     const int32_t  *order;             /* [n_reads] read indices, longest first (triage walks reads in this order)   */
     int32_t        *cand;              /* [n_reads] reads the triage kernel hands on to the locate kernel            */
+    int32_t        *cand_state;        /* [n_reads][4] per candidate: tracks done, max interval width, error, pad     */
     uint32_t       *counters;          /* [0] number of entries in cand[], [1] locate work counter; zeroed per pass   */
     void           *results;           /* ntl_read_result[n_reads]                                                */
     void           *stages;            /* ntl_stage[n_reads][3] or NULL                                           */

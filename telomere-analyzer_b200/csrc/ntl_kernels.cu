@@ -120,9 +120,7 @@ __device__ __forceinline__ void word_hits(const ntl_dev_pat &pt, const u32 (&pw)
     const bool fx = pt.fixed != 0;
 #pragma unroll 1
     for (int j = 0; j < pt.m; j++) {
-        const u32 nb = pt.nib[j];
-        const u32 mA = (nb & 1u) ? NTL_FULL : 0u, mC = (nb & 2u) ? NTL_FULL : 0u;
-        const u32 mG = (nb & 4u) ? NTL_FULL : 0u, mT = (nb & 8u) ? NTL_FULL : 0u;
+        const u32 mA = pt.mux4[j][0], mC = pt.mux4[j][1], mG = pt.mux4[j][2], mT = pt.mux4[j][3];
         u32 ew, en;
         if (fx) {
             ew = ~((pw[0] ^ mA) | (pw[1] ^ mC) | (pw[2] ^ mG) | (pw[3] ^ mT));
@@ -265,9 +263,16 @@ struct WinTab {                 /* the window table of one track (analyze_subtel
     int thr_reg, thr_last;      /* smallest telomeric count of a regular window / of this read's last window */
     bool any;                   /* at least one telomeric window on this track                                */
     const u32 *bits;            /* class bits of all windows (1 = telomeric) in shared memory, or NULL        */
+    const double *dens;         /* dens[c] = (double)c / (double)S, filled on the host with that division     */
 };
 __device__ __forceinline__ int wt_start(const WinTab &w, int k) { return 1 + k * w.S; }
 __device__ __forceinline__ int wt_end(const WinTab &w, int k) { return k == w.n - 1 ? w.L : (k + 1) * w.S; }
+__device__ __forceinline__ double wt_density_of_count(const WinTab &w, int k, int count)
+{
+    /* get_sub_density (NanoTel.R:467): count / width in double; width-S windows read the quotient from a table */
+    const int width = wt_end(w, k) - wt_start(w, k) + 1;
+    return width == w.S ? w.dens[count] : (double)count / (double)width;
+}
 __device__ __forceinline__ int wt_count(const WinTab &w, int k)
 {
     const u32 hi = w.cum[k], lo = k > 0 ? (u32)w.cum[k - 1] : 0u;
@@ -316,7 +321,7 @@ __device__ __noinline__ int run_scan(const WinTab &w, int i0, int i1, int dir, d
                 if (dir > 0 ? cur > i1 : cur < i1) break;
             }
             in_a_row += 1;
-            score = score + (double)wt_count(w, cur) / (double)(wt_end(w, cur) - wt_start(w, cur) + 1);   /* :1014 */
+            score = score + wt_density_of_count(w, cur, wt_count(w, cur));   /* :1014 */
             if (run_first == -1) run_first = cur;
             if ((double)in_a_row >= R && score >= T) { *first = run_first; return cur; }
             cur += dir;
@@ -356,7 +361,7 @@ __device__ __noinline__ int run_scan(const WinTab &w, int i0, int i1, int dir, d
                 const int idx = i0 + dir * (base + b);
                 const int c = __shfl_sync(NTL_FULL, cnt[u], b);
                 in_a_row += 1;
-                score = score + (double)c / (double)(wt_end(w, idx) - wt_start(w, idx) + 1);   /* :1014 */
+                score = score + wt_density_of_count(w, idx, c);   /* :1014 */
                 if (run_first == -1) run_first = idx;
                 if ((double)in_a_row >= R && score >= T) { *first = run_first; return idx; }
                 b += 1;
@@ -737,7 +742,11 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
         const int leader = __ffs((int)cm) - 1;
         if (lane == leader) base = (int)atomicAdd(&a.counters[0], (u32)__popc(cm));
         base = __shfl_sync(NTL_FULL, base, leader);
-        if (cand && sub == 0) a.cand[base + __popc(cm & ((1u << lane) - 1u))] = r;
+        if (cand && sub == 0) {
+            const int pos = base + __popc(cm & ((1u << lane) - 1u));
+            a.cand[pos] = r;
+            reinterpret_cast<int4 *>(a.cand_state)[pos] = make_int4(0, 0, 0, 0);
+        }
     }
 }
 
@@ -746,19 +755,23 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
  * ============================================================================================================= */
 #define NTL_BITS_WORDS 512          /* class bits of up to 16384 windows per warp in shared memory */
 
-__device__ void locate_read(const ntl_read_args &a, int r, int lane, u32 *sbits);
+__device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *state, int lane, u32 *sbits);
 
 __global__ void __launch_bounds__(128) ntl_locate_kernel(const ntl_read_args a)
 {
     __shared__ u32 s_bits[4][NTL_BITS_WORDS];
     const int lane = threadIdx.x & 31;
-    const int n_cand = (int)a.counters[0];
+    /* work item = (candidate read, track): the tracks of a read are independent until the keep rule, so they run
+     * on different warps; cand_state[c] = {tracks done, max interval width, error} joins them */
+    const int T = c_prm.n_tracks;
+    const int n_items = (int)a.counters[0] * T;
     for (;;) {
         int i = 0;
         if (lane == 0) i = (int)atomicAdd(&a.counters[1], 1u);
         i = __shfl_sync(NTL_FULL, i, 0);
-        if (i >= n_cand) break;
-        locate_read(a, a.cand[i], lane, s_bits[threadIdx.x >> 5]);
+        if (i >= n_items) break;
+        const int c = i / T;
+        locate_read(a, a.cand[c], i - c * T, a.cand_state + 4 * (size_t)c, lane, s_bits[threadIdx.x >> 5]);
     }
 }
 
@@ -799,7 +812,7 @@ __device__ __noinline__ bool warp_any_telomeric(const WinTab &w, int lane, u32 *
     return __any_sync(NTL_FULL, tel);
 }
 
-__device__ void locate_read(const ntl_read_args &a, int r, int lane, u32 *sbits)
+__device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *state, int lane, u32 *sbits)
 {
     ntl_read_result *res = reinterpret_cast<ntl_read_result *>(a.results) + r;
     ntl_stage *stg = a.stages ? reinterpret_cast<ntl_stage *>(a.stages) + (size_t)r * 3 : nullptr;
@@ -819,10 +832,11 @@ __device__ void locate_read(const ntl_read_args &a, int r, int lane, u32 *sbits)
     } else {
         bool err = false;
         int max_width = 0;
-        for (int t = 0; t < T && !err; t++) {
+        for (int t = t_only; t == t_only; t++) {
             WinTab w;
             w.cum = a.cum[t] + a.win_off[r]; w.n = n_win > 0 ? n_win : 0; w.S = S; w.L = rv.L;
             w.thr_reg = c_prm.thr_reg;
+            w.dens = a.dens;
             w.thr_last = w.n > 0 ? (int)a.thr[wt_end(w, w.n - 1) - wt_start(w, w.n - 1) + 1] : 0;
             w.bits = nullptr;
             __syncwarp();                                           /* the previous track is done with sbits */
@@ -872,14 +886,23 @@ __device__ void locate_read(const ntl_read_args &a, int r, int lane, u32 *sbits)
             const int wd = e2 - s2 + 1;
             if (wd > max_width) max_width = wd;
         }
-        if (err) status |= NTL_READ_REF_ERROR;
-        else if (max_width >= 30) status |= NTL_READ_KEEP;                                 /* :1847, :1857 */
-    }
-    if (lane == 0) {
-        res->status = status;
-        res->n_win = n_win > 0 ? n_win : 0;
-        for (int t = 0; t < 3; t++) res->track[t] = out[t];
-        res->win_offset = a.win_off[r];
+        /* ---- this warp's track is done; the warp that completes the read's last track writes the record head:
+         *      keep iff max interval width >= 30 over the tracks (:1847, :1857) */
+        if (lane == 0) {
+            res->track[t_only] = out[t_only];
+            if (err) atomicOr(&state[2], 1);
+            else atomicMax(&state[1], max_width);
+            __threadfence();
+            if (atomicAdd(&state[0], 1) == T - 1) {
+                const int any_err = atomicOr(&state[2], 0), mw = atomicMax(&state[1], 0);
+                if (any_err) status |= NTL_READ_REF_ERROR;
+                else if (mw >= 30) status |= NTL_READ_KEEP;
+                res->status = status;
+                res->n_win = n_win > 0 ? n_win : 0;
+                res->win_offset = a.win_off[r];
+                for (int t = T; t < 3; t++) res->track[t] = out[t];
+            }
+        }
     }
 }
 
