@@ -218,10 +218,22 @@ __device__ __noinline__ int local_count(const ReadView &rv, int t, int lo, int h
 /* =============================================================================================================
  * K4: edge filter (filter_reads / filter_density, NanoTel.R:2083-2163)
  * ============================================================================================================= */
+__device__ __forceinline__ u32 range_word_mask(int w, int vlo, int vhi)
+{
+    const int p0 = w << 5;
+    int lb = vlo - p0; if (lb < 0) lb = 0;
+    int hb = vhi - p0; if (hb > 31) hb = 31;
+    return hb < lb ? 0u : ((NTL_FULL >> (31 - hb)) & (NTL_FULL << lb));
+}
+
+/* Eight lanes per read, one word of the 200-base slice per lane (the slice spans at most 8 words): exact hits with
+ * fixed = FALSE (letters match iff their IUPAC sets intersect), union of the hit intervals, covered / 200. */
 __global__ void __launch_bounds__(256) ntl_filter_kernel(const ntl_read_args a)
 {
     const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int sub = lane & 7;
+    const u32 tmask = 0xffu << (lane & 24);
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     if (r >= a.n_reads) return;
     ReadView rv;
     rv.L = a.len[r]; rv.fmt = a.fmt[r]; rv.base = a.packed + a.woff[r]; rv.n_words = (rv.L >> 5) + 1;
@@ -230,28 +242,40 @@ __global__ void __launch_bounds__(256) ntl_filter_kernel(const ntl_read_args a)
         int lo, hi;
         if (c_prm.right_edge) { hi = rv.L - 70; lo = hi - 199; }   /* subseq(end = -(70+1), width = 200) :2131-2134 */
         else { lo = 71; hi = 270; }                                 /* subseq(start = 71, width = 200)   :2136       */
-        int covered = 0;
-        u32 hprev[NTL_DEV_MAX_PAT];
-        for (int p = 0; p < c_prm.n_main; p++) hprev[p] = 0u;
-        for (int p0 = lo; p0 <= hi; p0 += 32) {
-            u32 cov = 0u;
-            for (int p = 0; p < c_prm.n_main; p++) {                /* fixed = FALSE always, exact (:2091-2096) */
-                const ntl_dev_pat &pt = c_prm.main_pat[p];
-                const u32 h1 = hits32(rv, pt, 0, 0, p0, lo, hi, lane);
-                const unsigned long long H = ((unsigned long long)h1 << 32) | hprev[p];
-                unsigned long long D = H;
-                for (int j = 1; j < pt.m; j++) D |= H << j;
-                cov |= (u32)(D >> 32);
-                hprev[p] = h1;
+        const int w = (lo >> 5) + sub;
+        /* the slice is the whole subject of matchPattern: letters outside it do not exist (k = 0: no hit there) */
+        const u32 vw = range_word_mask(w, lo, hi), vn = range_word_mask(w + 1, lo, hi);
+        u32 pw[4], pn[4];
+        word_planes(rv, w, pw);
+        word_planes(rv, w + 1, pn);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { pw[k] &= vw; pn[k] &= vn; }
+        u32 cov = 0u;
+#pragma unroll 1
+        for (int p = 0; p < c_prm.n_main; p++) {                    /* fixed = FALSE always, exact (:2091-2096) */
+            const ntl_dev_pat &pt = c_prm.main_pat[p];
+            u32 mis = 0u;
+#pragma unroll 1
+            for (int j = 0; j < pt.m; j++) {
+                const u32 mA = pt.mux4[j][0], mC = pt.mux4[j][1], mG = pt.mux4[j][2], mT = pt.mux4[j][3];
+                const u32 ew = (pw[0] & mA) | (pw[1] & mC) | (pw[2] & mG) | (pw[3] & mT);
+                const u32 en = (pn[0] & mA) | (pn[1] & mC) | (pn[2] & mG) | (pn[3] & mT);
+                mis |= ~__funnelshift_r(ew, en, j);
             }
-            const int rem = hi - p0;
-            if (rem < 31) cov &= NTL_FULL >> (31 - rem);
-            covered += __popc(cov);
+            const u32 H = ~mis;
+            u32 Hp = __shfl_up_sync(tmask, H, 1, 8);
+            if (sub == 0) Hp = 0u;
+#pragma unroll 1
+            for (int j = 0; j < pt.m; j++) cov |= __funnelshift_l(Hp, H, j);
         }
+        int covered = __popc(cov & vw);
+        covered += __shfl_xor_sync(tmask, covered, 1, 8);
+        covered += __shfl_xor_sync(tmask, covered, 2, 8);
+        covered += __shfl_xor_sync(tmask, covered, 4, 8);
         const double total_density = (double)covered / (double)(hi - lo + 1);   /* :2100 */
         keep = total_density >= c_prm.filter_threshold ? 1 : 0;                  /* :2101, :2143 */
     }
-    if (lane == 0) a.pass[r] = (uint8_t)keep;
+    if (sub == 0) a.pass[r] = (uint8_t)keep;
 }
 
 /* =============================================================================================================
@@ -930,8 +954,7 @@ extern "C" cudaError_t ntl_k_scan_occupancy(int *blocks_per_sm)
 extern "C" cudaError_t ntl_k_filter(const ntl_read_args *a, cudaStream_t st)
 {
     if (a->n_reads <= 0) return cudaSuccess;
-    const int wpb = 8;
-    ntl_filter_kernel<<<(a->n_reads + wpb - 1) / wpb, wpb * 32, 0, st>>>(*a);
+    ntl_filter_kernel<<<(a->n_reads * 8 + 255) / 256, 256, 0, st>>>(*a);     /* 8 lanes per read */
     return cudaGetLastError();
 }
 
