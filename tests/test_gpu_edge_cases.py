@@ -1,0 +1,72 @@
+"""GPU: inputs at the edges of the implementation's internal limits, compared with the oracle bit for bit.
+
+* very long reads: more windows than the triage kernel walks (8192) and than the locate kernel keeps as class bits in
+  shared memory (16384) -> the global-memory fallback of the run/score machine;
+* an empty batch, a batch of one 1-base read, call-order errors."""
+import numpy as np
+import pytest
+
+from helpers import compare_batch, oracle_batch
+
+pytestmark = pytest.mark.gpu
+ACGT = np.frombuffer(b"ACGT", np.uint8)
+
+
+def _long_read(rng, L, telo_at_end, telo_len=12000, unit=b"TTAGGG"):
+    s = bytearray(rng.choice(ACGT, L).tobytes())
+    rep = bytearray((unit * (telo_len // len(unit) + 1))[:telo_len])
+    for _ in range(telo_len // 40):
+        rep[int(rng.integers(0, telo_len))] = ACGT[int(rng.integers(0, 4))]
+    if telo_at_end:
+        s[L - telo_len - 30:L - 30] = rep
+    else:
+        s[25:25 + telo_len] = rep
+    # a few isolated telomeric windows in the middle (runs that never qualify)
+    for pos in (L // 3, L // 2, L // 2 + 350):
+        s[pos:pos + 150] = (unit * 25)[:150]
+    return bytes(s)
+
+
+@pytest.mark.parametrize("S,L", [(100, 900_000), (100, 1_700_000), (20, 400_000), (500, 3_000_000)])
+def test_very_long_reads(S, L):
+    from nanotel_b200 import Scanner
+    rng = np.random.default_rng(L + S)
+    seqs = [_long_read(rng, L, True), _long_read(rng, L - 777, False), bytes(rng.choice(ACGT, L // 2)),
+            _long_read(rng, 5000, True, 2000)]
+    for right in (False, True):
+        P, recs, passed, win_off, wc = oracle_batch(seqs, "TTAGGG", "TTGGG", 0.6, S, right, False, False, n_threads=4)
+        with Scanner("TTAGGG", "TTGGG", 0.6, S, right_edge=right, debug_stages=True) as sc:
+            res = sc.scan(seqs)
+            compare_batch(sc, res, seqs, recs, passed, win_off, wc, check_stages=True, label="S=%d L=%d right=%s" % (S, L, right))
+            assert res[0]["status"] & 1 and res[1]["status"] & 1 and not (res[2]["status"] & 1)
+
+
+def test_empty_batch_and_tiny_reads():
+    from nanotel_b200 import NanoTelError, Scanner
+    with Scanner("TTAGGG") as sc:
+        res = sc.scan([])
+        assert len(res) == 0
+        res = sc.scan([b"A"])
+        assert len(res) == 1 and res[0]["n_win"] == 0 and not (res[0]["status"] & 1)
+        with pytest.raises(NanoTelError) as e:
+            sc.scan([b"ACGT", b""])
+        assert e.value.code == -3                                   # zero-length read: NanoTel.R stops (:216)
+        with pytest.raises(NanoTelError) as e:
+            sc.scan([b"ACGTJ"])
+        assert e.value.code == -3                                   # not a DNA letter
+        res = sc.scan([b"TTAGGG" * 50])                             # the context is still usable
+        assert res[0]["status"] & 1
+
+
+def test_call_order_is_checked():
+    from nanotel_b200 import NanoTelError, Scanner
+    with Scanner("TTAGGG") as sc:
+        with pytest.raises(NanoTelError) as e:
+            sc.run()
+        assert e.value.code == -7
+        sc.pack([b"TTAGGG" * 40])
+        with pytest.raises(NanoTelError):
+            sc.download()
+        sc.upload(); sc.run()
+        res = sc.download()
+        assert res[0]["status"] & 1
