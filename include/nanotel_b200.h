@@ -153,6 +153,19 @@ int ntl_get_windows(const ntl_ctx *ctx, int32_t read_idx, int32_t track, int32_t
 /* NTL_OPT_DEBUG_STAGES only: intermediate intervals of read read_idx, track. */
 int ntl_get_stages(const ntl_ctx *ctx, int32_t read_idx, int32_t track, ntl_stage *out);
 
+/* -- record reader (host side; replaces open_input_files + readDNAStringSet(files, nrec, format), NanoTel.R:2180, 2213)
+ * FASTA (multi-line) / FASTQ (4-line records), gzip transparent, records streamed nrec at a time across the file
+ * list, names = full header line without '>' / '@', qualities skipped.  A chunk is ONE contiguous sequence buffer
+ * + n+1 offsets (what ntl_scan_batch_concat takes) and one name buffer + n+1 offsets; both stay valid until the next
+ * ntl_reader_next / ntl_reader_close.  The following chunk is read by a background thread meanwhile. */
+typedef struct ntl_reader ntl_reader;
+int  ntl_reader_open(ntl_reader **reader, const char *const *paths, int32_t n_paths, const char *format);
+/* Returns the number of records of the chunk (0 = end of input) or a negative ntl_status. nrec <= 0: everything. */
+int32_t ntl_reader_next(ntl_reader *reader, int32_t nrec, const char **seq_buf, const int64_t **seq_off,
+                        const char **name_buf, const int64_t **name_off);
+const char *ntl_reader_error(const ntl_reader *reader);
+void ntl_reader_close(ntl_reader *reader);
+
 /* -- diagnostics ------------------------------------------------------------------------------------------ */
 /* NVRTC-compile the pattern-specialised scan kernel for `arch` ("sm_100a") without touching a device; optionally
  * write the cubin to cubin_path (for cuobjdump).  Returns the cubin size in bytes or a negative ntl_status. */

@@ -57,6 +57,7 @@ EXPORTS = [
     "ntl_version", "ntl_create", "ntl_destroy", "ntl_last_error", "ntl_scan_batch", "ntl_scan_batch_concat",
     "ntl_batch_pack", "ntl_batch_upload", "ntl_batch_run", "ntl_batch_enqueue", "ntl_batch_wait", "ntl_batch_download", "ntl_get_timings", "ntl_stream",
     "ntl_get_windows", "ntl_get_stages", "ntl_jit_compile_check", "ntl_pack_read", "ntl_assign_serials", "ntl_count_windows",
+    "ntl_reader_open", "ntl_reader_next", "ntl_reader_error", "ntl_reader_close",
 ]
 
 _lib = None
@@ -99,6 +100,13 @@ def load() -> C.CDLL:
     L.ntl_assign_serials.argtypes = [vp, i32, i32, vp, vp, C.POINTER(i32)]
     L.ntl_count_windows.argtypes = [i64, i32]
     L.ntl_count_windows.restype = i32
+    L.ntl_reader_open.argtypes = [C.POINTER(vp), C.POINTER(C.c_char_p), i32, C.c_char_p]
+    L.ntl_reader_next.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.ntl_reader_next.restype = i32
+    L.ntl_reader_error.argtypes = [vp]
+    L.ntl_reader_error.restype = C.c_char_p
+    L.ntl_reader_close.argtypes = [vp]
+    L.ntl_reader_close.restype = None
     _lib = L
     return L
 

@@ -101,7 +101,60 @@ def iter_chunks(paths: Sequence[str], fmt: str, nrec: int) -> Iterator[List[Read
         yield chunk
 
 
+class NativeReader:
+    """ntl_reader_*: the library's FASTA/FASTQ(+gzip) reader.  Iterating yields (names, buf, offsets) per chunk of
+    `nrec` records: one contiguous uint8 sequence buffer + n+1 offsets (copied out of the reader's buffers)."""
+
+    def __init__(self, paths: Sequence[str], fmt: str, nrec: int):
+        import ctypes as C
+        self._C = C
+        self._L = _lib.load()
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        self._h = C.c_void_p()
+        rc = self._L.ntl_reader_open(C.byref(self._h), arr, len(paths), fmt.encode())
+        if rc != 0:
+            raise ValueError('format should be "fastq" or "fasta"' if fmt not in ("fastq", "fasta") else "ntl_reader_open failed")
+        self.nrec = int(nrec)
+
+    def __iter__(self):
+        C = self._C
+        sb, so, nb, no = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        try:
+            while True:
+                n = self._L.ntl_reader_next(self._h, self.nrec, C.byref(sb), C.byref(so), C.byref(nb), C.byref(no))
+                if n < 0:
+                    raise ValueError(self._L.ntl_reader_error(self._h).decode(errors="replace"))
+                if n == 0:
+                    return
+                soff = np.ctypeslib.as_array(C.cast(so, C.POINTER(C.c_int64)), (n + 1,)).copy()
+                noff = np.ctypeslib.as_array(C.cast(no, C.POINTER(C.c_int64)), (n + 1,)).copy()
+                buf = np.ctypeslib.as_array(C.cast(sb, C.POINTER(C.c_uint8)), (max(int(soff[-1]), 1),)).copy()
+                nraw = C.string_at(nb, int(noff[-1])) if noff[-1] > 0 else b""
+                names = [nraw[int(noff[i]):int(noff[i + 1])].decode("utf-8", "replace") for i in range(n)]
+                yield names, buf, soff
+        finally:
+            self.close()
+
+    def close(self):
+        if self._h and self._h.value:
+            self._L.ntl_reader_close(self._h)
+            self._h = self._C.c_void_p()
+
+
 # ------------------------------------------------------------------------------------------------ tables
+class _LazyChunk:
+    """Sequence-of-(name, sequence) view over a reader chunk; sequences are materialised only for the kept reads."""
+
+    def __init__(self, names, buf, off):
+        self.names, self.buf, self.off = names, buf, off
+
+    def __len__(self):
+        return len(self.names)
+
+    def __getitem__(self, i):
+        return self.names[i], self.buf[int(self.off[i]):int(self.off[i + 1])].tobytes()
+
+
 def _tokens(p) -> List[str]:
     if p is None:
         return []
@@ -263,14 +316,14 @@ def run_future_worker_chuncks(input_path: str, output_path: Optional[str], forma
     serial_start = 1
     with Scanner(_tokens(patterns), _tokens(tvr_patterns) or None, min_density, subseq_length, rc=do_rc,
                  use_filter=use_filter, right_edge=right_edge, device=device) as sc:
-        for ci, chunk in enumerate(iter_chunks(files, format, nrec), 1):
+        for ci, (names, buf, soff) in enumerate(NativeReader(files, format, nrec), 1):
             if verbose:
                 print(time.strftime("%Y-%m-%d %H:%M:%S"))
                 print("processing chunk", ci, "...")
-            seqs = [s for _, s in chunk]
-            all_len.append(np.fromiter((len(s) for s in seqs), np.int64, len(seqs)))   # :2225 (before the filter)
-            res = sc.scan(seqs)
+            all_len.append(np.diff(soff))                                               # :2225 (before the filter)
+            res = sc.scan_concat(buf, soff)
             serial, order, serial_start = assign_serials(res, serial_start)             # :2234-2258
+            chunk = _LazyChunk(names, buf, soff)
             rows += _rows_from_results(chunk, res, serial, order, sc.n_tracks)
             if output_path:
                 write_read_outputs(output_path, chunk, sc, res, serial, order, rc_applied=do_rc)

@@ -1,0 +1,63 @@
+"""CPU: the native FASTA/FASTQ(+gzip) reader (ntl_reader_*) against the plain Python reader on awkward inputs:
+multi-line FASTA, CRLF line ends, blank lines, no trailing newline, several files, gzip and plain, nrec chunking."""
+import gzip
+
+import numpy as np
+import pytest
+
+
+def _native(paths, fmt, nrec):
+    from nanotel_b200.nanotel import NativeReader
+    out = []
+    for names, buf, off in NativeReader(paths, fmt, nrec):
+        out.append([(names[i], buf[int(off[i]):int(off[i + 1])].tobytes()) for i in range(len(names))])
+    return out
+
+
+def test_fasta_variants(tmp_path):
+    from nanotel_b200.nanotel import iter_chunks
+    a = tmp_path / "a.fasta"
+    a.write_bytes(b">r1 first read\nACGT\nACG\n\n>r2\r\nTTAGGG\r\nTT\r\n>r3 empty\n>r4\nGG")
+    b = tmp_path / "b.fa.gz"
+    with gzip.open(b, "wb") as f:
+        f.write(b"; comment line before the first header\n>z1\n" + b"ACGT" * 5000 + b"\n>z2\nA\n")
+    paths = [str(a), str(b)]
+    for nrec in (1, 2, 3, 100, 0):
+        got = _native(paths, "fasta", nrec)
+        exp = list(iter_chunks(paths, "fasta", nrec))
+        assert got == exp, nrec
+    flat = [r for c in _native(paths, "fasta", 0) for r in c]
+    assert [n for n, _ in flat] == ["r1 first read", "r2", "r3 empty", "r4", "z1", "z2"]
+    assert flat[0][1] == b"ACGTACG" and flat[1][1] == b"TTAGGGTT" and flat[2][1] == b"" and flat[3][1] == b"GG"
+
+
+def test_fastq_variants(tmp_path):
+    from nanotel_b200.nanotel import iter_chunks
+    rng = np.random.default_rng(3)
+    recs = [("read%05d len=%d" % (i, L), bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), L)))
+            for i, L in enumerate(rng.integers(1, 5000, 57))]
+    gz = tmp_path / "x.fastq.gz"
+    with gzip.open(gz, "wb") as f:
+        for n, s in recs[:30]:
+            f.write(b"@" + n.encode() + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    plain = tmp_path / "y.fastq"
+    with open(plain, "wb") as f:
+        for k, (n, s) in enumerate(recs[30:]):
+            f.write(b"@" + n.encode() + b"\r\n" + s + b"\r\n+" + n.encode() + b"\r\n" + b"@" * len(s) + (b"" if k == 26 else b"\r\n"))
+    paths = [str(gz), str(plain)]
+    for nrec in (1, 7, 30, 31, 1000):
+        got = _native(paths, "fastq", nrec)
+        assert got == list(iter_chunks(paths, "fastq", nrec))
+        assert [r for c in got for r in c] == recs
+
+
+def test_reader_errors(tmp_path):
+    from nanotel_b200.nanotel import NativeReader
+    bad = tmp_path / "bad.fastq"
+    bad.write_bytes(b"@r1\nACGT\n+\nIIII\nACGT\n")
+    with pytest.raises(ValueError):
+        list(NativeReader([str(bad)], "fastq", 10))
+    with pytest.raises(ValueError):
+        NativeReader([str(bad)], "bam", 10)
+    with pytest.raises(ValueError):
+        list(NativeReader([str(tmp_path / "missing.fastq")], "fastq", 10))
