@@ -283,11 +283,10 @@ def write_read_outputs(output_dir: str, reads: Sequence[Read], sc: Scanner, res:
         if rc_applied:
             seq = revcomp(seq)
         s = int(serial[i])
-        with gzip.open(os.path.join(rd, "%d.fasta.gz" % s), "wb") as f:
-            f.write(b">" + name.encode() + b"\n")
-            up = seq.upper()
-            for k in range(0, len(up), 80):
-                f.write(up[k:k + 80] + b"\n")
+        up = seq.upper()
+        body = b"\n".join(up[k:k + 80] for k in range(0, len(up), 80))
+        with gzip.open(os.path.join(rd, "%d.fasta.gz" % s), "wb", compresslevel=6) as f:      # R's gzfile() default
+            f.write(b">" + name.encode() + b"\n" + body + b"\n")
         cols, header = [], ["ID", "start_index", "end_index"]
         for t, suffix in zip(range(sc.n_tracks), ("", "_mismatch", "_mismatch_tvr")):
             st, en, cov, den = sc.windows(int(i), t, int(res[i]["n_win"]))
