@@ -83,11 +83,13 @@ __device__ __forceinline__ void ntl_ldg256(const u32 *p, u32 (&v)[8])
                  : "l"(p));
 }
 
-/* bits b of the word starting at bit index wpos with 1 <= wpos + b <= L */
+/* bits b of the word starting at bit index wpos with 1 <= wpos + b <= L: the low  clamp(L - wpos + 1, 0, 32)  bits
+ * (one clamped funnel shift), minus bit 0 of the read's very first word (the pad position) */
 __device__ __forceinline__ u32 ntl_valid_word(int wpos, int L)
 {
-    int rem = L - wpos;
-    u32 m = rem >= 31 ? NTL_FULL : (rem < 0 ? 0u : ((2u << rem) - 1u));
+    int nb = L - wpos + 1;
+    if (nb < 0) nb = 0;
+    u32 m = __funnelshift_lc(NTL_FULL, 0u, nb);
     if (wpos == 0) m &= ~1u;
     return m;
 }
@@ -108,6 +110,39 @@ __device__ __forceinline__ void ntl_group3(int n, u32 a, u32 b, u32 c, u32 &ex, 
     else { ex = a & b & c; le = (a & b) | (a & c) | (b & c); }
 }
 
+/* Funnel shifts.  The scan kernel is bound by the integer ALU pipe (LOP3 / SHF), while the FMA pipe idles: with
+ * NTL_FSHIFT_IMAD the shifts are computed there instead, as  (lo >> j) | (hi << (32 - j))  =  mulhi(lo, K) + hi * K
+ * with K = 2^(32-j) read from constant memory (so that the compiler cannot turn the multiplications back into shifts). */
+#ifdef NTL_FSHIFT_IMAD
+__constant__ u32 ntl_pow2[33] = {1u, 2u, 4u, 8u, 16u, 32u, 64u, 128u, 256u, 512u, 1024u, 2048u, 4096u, 8192u, 16384u,
+                                 32768u, 65536u, 131072u, 262144u, 524288u, 1048576u, 2097152u, 4194304u, 8388608u,
+                                 16777216u, 33554432u, 67108864u, 134217728u, 268435456u, 536870912u, 1073741824u,
+                                 2147483648u, 0u};
+__device__ __forceinline__ u32 ntl_fsr(u32 lo, u32 hi, int j)          /* low word of (hi:lo) >> j, 0 <= j < 32 */
+{
+#ifdef NTL_FSHIFT_IMAD_ALIGN
+    if (j == 0) return lo;
+    const u32 K = ntl_pow2[32 - j];
+    return __umulhi(lo, K) + hi * K;
+#else
+    return __funnelshift_r(lo, hi, j);
+#endif
+}
+__device__ __forceinline__ u32 ntl_fsl(u32 lo, u32 hi, int j)          /* high word of (hi:lo) << j, 0 <= j < 32 */
+{
+#ifdef NTL_FSHIFT_IMAD_DILATE
+    if (j == 0) return hi;
+    const u32 K = ntl_pow2[j];
+    return __umulhi(lo, K) + hi * K;
+#else
+    return __funnelshift_l(lo, hi, j);
+#endif
+}
+#else
+__device__ __forceinline__ u32 ntl_fsr(u32 lo, u32 hi, int j) { return __funnelshift_r(lo, hi, j); }
+__device__ __forceinline__ u32 ntl_fsl(u32 lo, u32 hi, int j) { return __funnelshift_l(lo, hi, j); }
+#endif
+
 /* Dilate hit starts forward by m positions, in place, over 5 words (word 4 receives the spill of word 3). */
 __device__ __forceinline__ void ntl_dilate5(u32 (&d)[5], int m)
 {
@@ -115,20 +150,20 @@ __device__ __forceinline__ void ntl_dilate5(u32 (&d)[5], int m)
     while (3 * w <= m) {            /* width w -> 3 w: two shifts and one three-input OR (a single LOP3) per word */
 #pragma unroll
         for (int i = 4; i >= 1; i--)
-            d[i] = d[i] | __funnelshift_l(d[i - 1], d[i], w) | __funnelshift_l(d[i - 1], d[i], 2 * w);
+            d[i] = d[i] | ntl_fsl(d[i - 1], d[i], w) | ntl_fsl(d[i - 1], d[i], 2 * w);
         d[0] = d[0] | (d[0] << w) | (d[0] << (2 * w));
         w *= 3;
     }
     while (2 * w <= m) {
 #pragma unroll
-        for (int i = 4; i >= 1; i--) d[i] |= __funnelshift_l(d[i - 1], d[i], w);
+        for (int i = 4; i >= 1; i--) d[i] |= ntl_fsl(d[i - 1], d[i], w);
         d[0] |= d[0] << w;
         w *= 2;
     }
     int s = m - w;
     if (s > 0) {
 #pragma unroll
-        for (int i = 4; i >= 1; i--) d[i] |= __funnelshift_l(d[i - 1], d[i], s);
+        for (int i = 4; i >= 1; i--) d[i] |= ntl_fsl(d[i - 1], d[i], s);
         d[0] |= d[0] << s;
     }
 }
@@ -163,7 +198,7 @@ __device__ __forceinline__ void ntl_letter(int p, int j, const u32 (&pl)[NPL][5]
         e[i] = TVR ? ntl_jit_eq_tvr(p, j, pl[1][i], pl[0][i], v[i]) : ntl_jit_eq_main(p, j, pl[1][i], pl[0][i], v[i]);
 #endif
 #pragma unroll
-    for (int i = 0; i < 4; i++) x[i] = __funnelshift_r(e[i], e[i + 1], j);
+    for (int i = 0; i < 4; i++) x[i] = ntl_fsr(e[i], e[i + 1], j);
 }
 
 /* hit-start masks of one pattern over the lane's 4 words: EX = exact, LE = at most one mismatch */
@@ -214,6 +249,10 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
     u32 run[3] = {0u, 0u, 0u};                     /* covered bases before this chunk (warp-uniform)          */
     int kq = kq_init, off = off_init;              /* first multiple of S at or after this lane's first bit   */
 
+    const u32 *qp = base + (size_t)lane * QW;
+    uint16_t *cump[3];                             /* this read's first window in each track's prefix plane   */
+#pragma unroll
+    for (int t = 0; t < 3; t++) cump[t] = t < T ? a.cum[t] + wo : nullptr;
     u32 cur[QW], nxt[QW];
 #pragma unroll
     for (int i = 0; i < QW; i++) cur[i] = 0u;
@@ -228,13 +267,14 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
     for (int c = 0; c < n_chunks; c++) {
         /* ---- prefetch the next chunk's quad */
         const int qn = (c + 1) * 32 + lane;
+        qp += 32 * QW;                                         /* this lane's quad of the next chunk */
 #pragma unroll
         for (int i = 0; i < QW; i++) nxt[i] = 0u;
         if (qn < n_quads) {
-            if constexpr (NPL == 2) ntl_ldg256(base + (size_t)qn * 8, *reinterpret_cast<u32(*)[8]>(&nxt[0]));
+            if constexpr (NPL == 2) ntl_ldg256(qp, *reinterpret_cast<u32(*)[8]>(&nxt[0]));
             else {
-                ntl_ldg256(base + (size_t)qn * 16, *reinterpret_cast<u32(*)[8]>(&nxt[0]));
-                ntl_ldg256(base + (size_t)qn * 16 + 8, *reinterpret_cast<u32(*)[8]>(&nxt[8]));
+                ntl_ldg256(qp, *reinterpret_cast<u32(*)[8]>(&nxt[0]));
+                ntl_ldg256(qp + 8, *reinterpret_cast<u32(*)[8]>(&nxt[8]));
             }
         }
 
@@ -252,7 +292,12 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
         u32 v[5];
         if (c == 0 || c + 2 >= n_chunks) {                     /* only the read's ends have invalid positions */
 #pragma unroll
-            for (int i = 0; i < 5; i++) v[i] = ntl_valid_word(pos0 + 32 * i, L);
+            for (int i = 0; i < 5; i++) {
+                int nb = L - (pos0 + 32 * i) + 1;
+                if (nb < 0) nb = 0;
+                v[i] = __funnelshift_lc(NTL_FULL, 0u, nb);
+            }
+            if (pos0 == 0) v[0] &= ~1u;                                /* position 0 is the pad bit */
         } else {
 #pragma unroll
             for (int i = 0; i < 5; i++) v[i] = NTL_FULL;
@@ -374,7 +419,7 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
                                                         __funnelshift_rc(cov[t][2], cov[t][3], sh1), sh2);
                         const u32 bf = (pre[t] >> (8 * wi)) & 0xffu;
                         const u32 val = ex[t] + bf + (u32)__popc(wv & bm);
-                        if (act) a.cum[t][wo + idx] = (uint16_t)val;
+                        if (act) cump[t][idx] = (uint16_t)val;
                     }
                 }
             }
