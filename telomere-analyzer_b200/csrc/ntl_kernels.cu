@@ -89,7 +89,7 @@ __device__ __forceinline__ int pat_mismatches(const ntl_dev_pat &pt, bool fixed,
  * (Biostrings::matchPattern, App. B.2/B.3): positions outside [vlo, vhi] are mismatches.
  * mode_fixed < 0: use the pattern's own fixed flag. */
 __device__ __forceinline__ u32 hits32(const ReadView &rv, const ntl_dev_pat &pt, int k, int mode_fixed, int p0, int vlo,
-                                      int vhi, int lane)
+                                   int vhi, int lane)
 {
     u32 pl[4];
     rv_fetch4(rv, p0 + lane, vlo, vhi, pl);
@@ -281,6 +281,10 @@ __global__ void __launch_bounds__(256) ntl_filter_kernel(const ntl_read_args a)
 /* =============================================================================================================
  * K3: locator
  * ============================================================================================================= */
+/* one copy of the IEEE double division (a ~80-instruction sequence) for the whole locate kernel: code size is what
+ * this kernel stalls on */
+__device__ __noinline__ double k3_div(double a, double b) { return a / b; }
+
 struct WinTab {                 /* the window table of one track (analyze_subtelos :737-764), never materialised */
     const uint16_t *cum;
     int n, S, L;
@@ -295,7 +299,7 @@ __device__ __forceinline__ double wt_density_of_count(const WinTab &w, int k, in
 {
     /* get_sub_density (NanoTel.R:467): count / width in double; width-S windows read the quotient from a table */
     const int width = wt_end(w, k) - wt_start(w, k) + 1;
-    return width == w.S ? w.dens[count] : (double)count / (double)width;
+    return width == w.S ? w.dens[count] : k3_div((double)count, (double)width);
 }
 __device__ __forceinline__ int wt_count(const WinTab &w, int k)
 {
@@ -323,12 +327,18 @@ __device__ __noinline__ int run_scan(const WinTab &w, int i0, int i1, int dir, d
     double score = 0.0;
     int run_first = -1, in_a_row = 0;
     const int total = (i1 - i0) * dir + 1;
-    if (w.bits != nullptr) {
-        /* class bits are in shared memory: walk them word by word, skipping runs of non-telomeric windows with
-         * ffs / clz; only the windows that enter a score are read back (warp-uniform) */
+    {
+        /* class bits (1 = telomeric) are walked word by word, skipping runs of non-telomeric windows with ffs / clz;
+         * only the windows that enter a score are read back (warp-uniform).  The bits sit in shared memory, or, for
+         * reads with more windows than fit there, are rebuilt 32 at a time with a ballot. */
         int cur = i0;
         while (dir > 0 ? cur <= i1 : cur >= i1) {
-            const u32 word = w.bits[cur >> 5];
+            u32 word;
+            if (w.bits != nullptr) word = w.bits[cur >> 5];
+            else {
+                const int k = ((cur >> 5) << 5) + lane;
+                word = __ballot_sync(NTL_FULL, k < w.n && wt_telo_count(w, k, wt_count(w, k < w.n ? k : 0)));
+            }
             int z;
             if (dir > 0) {
                 const u32 m = word >> (cur & 31);
@@ -353,47 +363,6 @@ __device__ __noinline__ int run_scan(const WinTab &w, int i0, int i1, int dir, d
         *first = run_first;
         return -1;
     }
-    /* 128 windows per step: four independent loads per lane are in flight before the first ballot */
-    for (int done = 0; done < total; done += 128) {
-        int cnt[4];
-        u32 mask[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int o = done + 32 * u + lane;
-            cnt[u] = o < total ? wt_count(w, i0 + dir * o) : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int o = done + 32 * u + lane;
-            mask[u] = __ballot_sync(NTL_FULL, cnt[u] >= 0 && wt_telo_count(w, i0 + dir * o, cnt[u]));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int base = done + 32 * u;
-            if (base >= total) break;
-            if (mask[u] == 0u) { score = 0.0; run_first = -1; in_a_row = 0; continue; }
-            const int nvalid = total - base < 32 ? total - base : 32;
-            int b = 0;
-            while (b < nvalid) {
-                if (!((mask[u] >> b) & 1u)) {
-                    score = 0.0; run_first = -1; in_a_row = 0;
-                    const u32 rest = mask[u] >> b;
-                    if (rest == 0u) break;
-                    b += __ffs((int)rest) - 1;
-                    continue;
-                }
-                const int idx = i0 + dir * (base + b);
-                const int c = __shfl_sync(NTL_FULL, cnt[u], b);
-                in_a_row += 1;
-                score = score + wt_density_of_count(w, idx, c);   /* :1014 */
-                if (run_first == -1) run_first = idx;
-                if ((double)in_a_row >= R && score >= T) { *first = run_first; return idx; }
-                b += 1;
-            }
-        }
-    }
-    *first = run_first;
-    return -1;
 }
 
 /* find_telo_position (NanoTel.R:973-1077) */
@@ -419,49 +388,34 @@ __device__ __noinline__ void find_telo_position(const WinTab &w, double R, doubl
     *ps = start; *pe = end;
 }
 
-/* find_left_telo (NanoTel.R:906-959) */
-__device__ __noinline__ void find_left_telo(const WinTab &w, int *ps, int *pe)
+/* find_left_telo (NanoTel.R:906-959) and find_right_telo (NanoTel.R:843-899) are mirror images: walk from the chosen
+ * edge (right = false: window 0 upward, true: window n-1 downward) to the first telomeric window, give up as soon as
+ * a window lies more than max_diff = 200 from that edge, then extend over the telomeric run.  n == 0 with the right
+ * edge is the caller's REF_ERROR case. */
+__device__ __noinline__ void find_edge_telo(const WinTab &w, bool right, int *ps, int *pe)
 {
-    int start = 1, end = 1, last_i = 0;
     const int n = w.n;
-    if (!w.any) {                       /* no telomeric window anywhere: only the max_diff = 200 test can fire */
-        const bool far = n > 0 && wt_start(w, n - 1) > 200;
+    if (!w.any) {                       /* no telomeric window anywhere: only the max_diff test can fire */
+        const bool far = n > 0 && (right ? wt_end(w, 0) < w.L - 200 : wt_start(w, n - 1) > 200);
         *ps = far ? -1 : 1; *pe = far ? -1 : 1;
         return;
     }
-    for (int i = 0; i < n; i++) {
-        if (wt_start(w, i) > 200) { *ps = -1; *pe = -1; return; }
-        if (!wt_telo(w, i)) continue;
-        start = wt_start(w, i); last_i = i; break;
-    }
-    for (int i = last_i; i < n; i++) {
-        if (!wt_telo(w, i)) break;
-        end = wt_end(w, i);
-    }
-    if (start > end) end = start + (wt_end(w, last_i) - wt_start(w, last_i));
-    *ps = start; *pe = end;
-}
-
-/* find_right_telo (NanoTel.R:843-899); n == 0 is the caller's REF_ERROR case */
-__device__ __noinline__ void find_right_telo(const WinTab &w, int *ps, int *pe)
-{
+    const int dir = right ? -1 : 1;
     int start = 1, end = 1, last_i = 0;
-    const int n = w.n;
-    if (!w.any) {
-        const bool far = n > 0 && wt_end(w, 0) < w.L - 200;
-        *ps = far ? -1 : 1; *pe = far ? -1 : 1;
-        return;
-    }
-    for (int i = n - 1; i >= 0; i--) {
-        if (wt_end(w, i) < w.L - 200) { *ps = -1; *pe = -1; return; }
+    for (int i = right ? n - 1 : 0; i >= 0 && i < n; i += dir) {
+        if (right ? wt_end(w, i) < w.L - 200 : wt_start(w, i) > 200) { *ps = -1; *pe = -1; return; }
         if (!wt_telo(w, i)) continue;
-        end = wt_end(w, i); last_i = i; break;
+        if (right) end = wt_end(w, i); else start = wt_start(w, i);
+        last_i = i;
+        break;
     }
-    for (int i = last_i; i >= 0; i--) {
+    const int anchor = last_i;          /* find_left_telo keeps last_i_start (:937), find_right_telo moves last_i (:886) */
+    for (int i = last_i; i >= 0 && i < n; i += dir) {
         if (!wt_telo(w, i)) break;
-        start = wt_start(w, i); last_i = i;
+        if (right) { start = wt_start(w, i); last_i = i; } else end = wt_end(w, i);
     }
-    if (start > end) end = start + (wt_end(w, last_i) - wt_start(w, last_i));
+    const int ref = right ? last_i : anchor;
+    if (start > end) end = start + (wt_end(w, ref) - wt_start(w, ref));
     *ps = start; *pe = end;
 }
 
@@ -489,7 +443,7 @@ __device__ __noinline__ int covered_in(const ReadView &rv, const WinTab &w, int 
 __device__ __forceinline__ double density_of(const ReadView &rv, const WinTab &w, int t, int a, int b, int lane)
 {
     const int cv = covered_in(rv, w, t, a, b, lane);
-    return cv == 0 ? 0.0 : (double)cv / (double)(b - a + 1);      /* 0 / width is +0.0 exactly */
+    return cv == 0 ? 0.0 : k3_div((double)cv, (double)(b - a + 1));      /* 0 / width is +0.0 exactly */
 }
 
 /* get_accurate_end (NanoTel.R:1692-1721).  `ranges` are the raw exact hits of the single fixed pattern on track A
@@ -531,7 +485,7 @@ __device__ __noinline__ int get_accurate_start(const ReadView &rv, int t, int te
         st = cov & ~((cov << 1) | (pv >> 31));
     }
     const int c50 = lanes_popc(cov, wb, lane, s, s + 49);
-    const double first_50 = (double)c50 / 50.0;                         /* IRanges(start, width = 50) :1732 */
+    const double first_50 = k3_div((double)c50, 50.0);                         /* IRanges(start, width = 50) :1732 */
     if (first_50 < 0.3) {
         const int a = lanes_min(st, wb, lane, s + 48, s + 99);
         if (a != NTL_NONE) telo_start = a;
@@ -890,8 +844,8 @@ __device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *stat
             if (te - ts + 1 < 100) {                                                       /* :1129-1136 */
                 if (c_prm.right_edge) {
                     if (w.n == 0) { err = true; break; }                                   /* R stops at :859-861 */
-                    find_right_telo(w, &ts, &te);
-                } else find_left_telo(w, &ts, &te);
+                    find_edge_telo(w, true, &ts, &te);
+                } else find_edge_telo(w, false, &ts, &te);
             }
             if (stg && lane == 0) {
                 ntl_stage s;
