@@ -253,6 +253,16 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
     uint16_t *cump[3];                             /* this read's first window in each track's prefix plane   */
 #pragma unroll
     for (int t = 0; t < 3; t++) cump[t] = t < T ? a.cum[t] + wo : nullptr;
+    uint16_t *wp[3];                               /* &cump[t][kq - 1]: this lane's first regular window end   */
+#pragma unroll
+    for (int t = 0; t < 3; t++) wp[t] = cump[t] + (kq_init - 1);
+    const u32 v0_first = lane == 0 ? ~1u : NTL_FULL;
+    u32 ge[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {                  /* opaque 0/1 factors: keeps the warp scan's adds as IMADs  */
+        const u32 g = lane >= (1 << k) ? 1u : 0u;
+        asm("mov.u32 %0, %1;" : "=r"(ge[k]) : "r"(g));
+    }
     u32 cur[QW], nxt[QW];
 #pragma unroll
     for (int i = 0; i < QW; i++) cur[i] = 0u;
@@ -290,18 +300,18 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
         }
         const int pos0 = (c * 32 + lane) * NTL_LANE_BITS;      /* bit index = 1-based position */
         u32 v[5];
-        if (c == 0 || c + 2 >= n_chunks) {                     /* only the read's ends have invalid positions */
+        if ((c + 1) * NTL_CHUNK_BITS + 32 > L) {               /* only the read's tail has positions beyond L */
 #pragma unroll
             for (int i = 0; i < 5; i++) {
                 int nb = L - (pos0 + 32 * i) + 1;
                 if (nb < 0) nb = 0;
                 v[i] = __funnelshift_lc(NTL_FULL, 0u, nb);
             }
-            if (pos0 == 0) v[0] &= ~1u;                                /* position 0 is the pad bit */
         } else {
 #pragma unroll
             for (int i = 0; i < 5; i++) v[i] = NTL_FULL;
         }
+        if (c == 0) v[0] &= v0_first;                          /* position 0 is the pad bit */
 
         u32 cov[3][5];
 #pragma unroll
@@ -370,12 +380,12 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
         /* ---- packed warp scan: (A | B << 16) and C; each lane total <= 128, chunk total <= 4096 */
         u32 s01 = tot[0] | (tot[1] << 16), s2 = tot[2];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            u32 y01 = __shfl_up_sync(NTL_FULL, s01, d);
-            if (lane >= d) s01 += y01;
+        for (int k = 0; k < 5; k++) {                          /* s += (lane >= 2^k) * y: one IMAD, off the ALU pipe */
+            u32 y01 = __shfl_up_sync(NTL_FULL, s01, 1 << k);
+            s01 = y01 * ge[k] + s01;
             if (T == 3) {
-                u32 y2 = __shfl_up_sync(NTL_FULL, s2, d);
-                if (lane >= d) s2 += y2;
+                u32 y2 = __shfl_up_sync(NTL_FULL, s2, 1 << k);
+                s2 = y2 * ge[k] + s2;
             }
         }
         u32 ex[3];
@@ -408,25 +418,42 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
                 act = rel >= 0 && rel < NTL_LANE_BITS;
             }
             {
-                /* branch-free: word (rel >> 5) of the lane's four is picked with clamped funnel shifts */
-                const int wi = (rel >> 5) & 3;
-                const u32 bm = NTL_FULL >> (31 - (rel & 31));
-                const int sh1 = (wi & 1) << 5, sh2 = (wi & 2) << 4;
+                const u32 bm = __funnelshift_r(NTL_FULL, 0u, ~rel);      /* bits 0 .. rel & 31 */
+                if (it < n_ends && ((it * S) >> 5) >= 3) {
+                    /* an active end of this rank can only lie in the lane's last word */
 #pragma unroll
-                for (int t = 0; t < 3; t++) {
-                    if (t < T) {
-                        const u32 wv = __funnelshift_rc(__funnelshift_rc(cov[t][0], cov[t][1], sh1),
-                                                        __funnelshift_rc(cov[t][2], cov[t][3], sh1), sh2);
-                        const u32 bf = (pre[t] >> (8 * wi)) & 0xffu;
-                        const u32 val = ex[t] + bf + (u32)__popc(wv & bm);
-                        if (act) cump[t][idx] = (uint16_t)val;
+                    for (int t = 0; t < 3; t++) {
+                        if (t < T) {
+                            const u32 val = ex[t] + (pre[t] >> 24) + (u32)__popc(cov[t][3] & bm);
+                            if (act) wp[t][it] = (uint16_t)val;
+                        }
+                    }
+                } else {
+                    /* branch-free: word (rel >> 5) of the lane's four is picked with clamped funnel shifts, the
+                     * count before it with one byte permute */
+                    const int sh1 = rel & 32, sh2 = rel & 64;  /* shift counts clamp at 32: 64 selects the high word */
+                    const u32 bsel = 0x4440u + ((u32)rel >> 5);  /* active ends have 0 <= rel < 128 */
+#pragma unroll
+                    for (int t = 0; t < 3; t++) {
+                        if (t < T) {
+                            const u32 wv = __funnelshift_rc(__funnelshift_rc(cov[t][0], cov[t][1], sh1),
+                                                            __funnelshift_rc(cov[t][2], cov[t][3], sh1), sh2);
+                            const u32 val = ex[t] + __byte_perm(pre[t], 0u, bsel) + (u32)__popc(wv & bm);
+                            if (act) { if (it < n_ends) wp[t][it] = (uint16_t)val; else cump[t][idx] = (uint16_t)val; }
+                        }
                     }
                 }
             }
         }
         /* ---- advance this lane's window-end cursor by one chunk (4096 = adv_a * S + adv_b) */
-        if (off >= adv_b) { off -= adv_b; kq += adv_a; }
-        else { off += S - adv_b; kq += adv_a + 1; }
+        {
+            const bool wrap = off < adv_b;
+            const int adv = adv_a + (wrap ? 1 : 0);
+            off += wrap ? S - adv_b : -adv_b;
+            kq += adv;
+#pragma unroll
+            for (int t = 0; t < 3; t++) if (t < T) wp[t] += adv;
+        }
 
 #pragma unroll
         for (int i = 0; i < QW; i++) cur[i] = nxt[i];
