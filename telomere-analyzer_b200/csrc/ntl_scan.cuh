@@ -143,27 +143,32 @@ __device__ __forceinline__ u32 ntl_fsr(u32 lo, u32 hi, int j) { return __funnels
 __device__ __forceinline__ u32 ntl_fsl(u32 lo, u32 hi, int j) { return __funnelshift_l(lo, hi, j); }
 #endif
 
-/* Dilate hit starts forward by m positions, in place, over 5 words (word 4 receives the spill of word 3). */
+/* Dilate hit starts forward by m positions, in place, over the lane's 4 words; word 4 receives what spills past them:
+ * its bit k is set iff a hit starts in the top m - 1 - k bits of word 3, i.e. it is those m - 1 bits smeared towards
+ * bit 0 (count-leading-zeros on the XU pipe plus one clamped shift instead of a fifth dilation). */
 __device__ __forceinline__ void ntl_dilate5(u32 (&d)[5], int m)
 {
+    u32 lz;                         /* leading zeros of those bits; 0xffffffff if none is set, which clamps to 32 */
+    asm("bfind.shiftamt.u32 %0, %1;" : "=r"(lz) : "r"(__funnelshift_rc(d[3], 0u, 33 - m)));
+    d[4] = __funnelshift_rc(NTL_FULL, 0u, lz);
     int w = 1;
     while (3 * w <= m) {            /* width w -> 3 w: two shifts and one three-input OR (a single LOP3) per word */
 #pragma unroll
-        for (int i = 4; i >= 1; i--)
+        for (int i = 3; i >= 1; i--)
             d[i] = d[i] | ntl_fsl(d[i - 1], d[i], w) | ntl_fsl(d[i - 1], d[i], 2 * w);
         d[0] = d[0] | (d[0] << w) | (d[0] << (2 * w));
         w *= 3;
     }
     while (2 * w <= m) {
 #pragma unroll
-        for (int i = 4; i >= 1; i--) d[i] |= ntl_fsl(d[i - 1], d[i], w);
+        for (int i = 3; i >= 1; i--) d[i] |= ntl_fsl(d[i - 1], d[i], w);
         d[0] |= d[0] << w;
         w *= 2;
     }
     int s = m - w;
     if (s > 0) {
 #pragma unroll
-        for (int i = 4; i >= 1; i--) d[i] |= ntl_fsl(d[i - 1], d[i], s);
+        for (int i = 3; i >= 1; i--) d[i] |= ntl_fsl(d[i - 1], d[i], s);
         d[0] |= d[0] << s;
     }
 }
