@@ -319,49 +319,69 @@ __device__ __forceinline__ bool wt_telo(const WinTab &w, int k)
     return wt_telo_count(w, k, wt_count(w, k));
 }
 
+/* First window at or after `cur` in direction dir (+1 / -1), not beyond i1, whose class bit equals `want`; i1 + dir if
+ * there is none.  With the class bits in shared memory every lane looks at one word, so a step covers 1024 windows;
+ * reads with more windows than fit there rebuild one word per step with a ballot. */
+__device__ __noinline__ int next_window(const WinTab &w, int cur, int i1, int dir, bool want, int lane)
+{
+    const int nw = (w.n + 31) >> 5;
+    const u32 flip = want ? 0u : NTL_FULL;
+    const bool par = w.bits != nullptr;
+    for (;;) {
+        if (dir > 0 ? cur > i1 : cur < i1) return i1 + dir;
+        const int off = par ? lane : 0;
+        const int wi = (cur >> 5) + dir * off;
+        u32 word = 0u;
+        if (par) { if (wi >= 0 && wi < nw) word = w.bits[wi] ^ flip; }
+        else {
+            const int k = (wi << 5) + lane;
+            word = __ballot_sync(NTL_FULL, k < w.n && wt_telo_count(w, k, wt_count(w, k < w.n ? k : 0))) ^ flip;
+        }
+        if (off == 0) word &= dir > 0 ? (NTL_FULL << (cur & 31)) : (NTL_FULL >> (31 - (cur & 31)));
+        const u32 nz = par ? __ballot_sync(NTL_FULL, word != 0u) : (word != 0u ? 1u : 0u);
+        if (nz == 0u) {
+            const int adv = par ? 32 : 1;
+            cur = dir > 0 ? ((cur >> 5) + adv) << 5 : (((cur >> 5) - adv + 1) << 5) - 1;
+            continue;
+        }
+        const int src = __ffs((int)nz) - 1;
+        if (par) word = __shfl_sync(NTL_FULL, word, src);
+        const int pos = (((cur >> 5) + dir * src) << 5) + (dir > 0 ? __ffs((int)word) - 1 : 31 - __clz((int)word));
+        return (dir > 0 ? pos > i1 : pos < i1) ? i1 + dir : pos;
+    }
+}
+
 /* The run/score machine of find_telo_position (NanoTel.R:1003-1025 forward, :1046-1068 backward) over windows
  * i0, i0+dir, ..., i1 (0-based, inclusive).  Returns the window index at which  in_a_row >= R && score >= T  first
- * holds, or -1; *first = first window of the run that is open when the scan stops (-1 if none). */
+ * holds, or -1; *first = first window of the run that is open when the scan stops (-1 if none).
+ * in_a_row and score restart at every non-telomeric window, so the machine is evaluated run by run: runs are found
+ * with next_window(), runs shorter than R are skipped without touching their densities, and the fp64 score of a
+ * longer run is summed in window order (lanes fetch 32 densities at a time, the sum itself is sequential as in R). */
 __device__ __noinline__ int run_scan(const WinTab &w, int i0, int i1, int dir, double R, double T, int *first, int lane)
 {
-    double score = 0.0;
-    int run_first = -1, in_a_row = 0;
-    const int total = (i1 - i0) * dir + 1;
-    {
-        /* class bits (1 = telomeric) are walked word by word, skipping runs of non-telomeric windows with ffs / clz;
-         * only the windows that enter a score are read back (warp-uniform).  The bits sit in shared memory, or, for
-         * reads with more windows than fit there, are rebuilt 32 at a time with a ballot. */
-        int cur = i0;
-        while (dir > 0 ? cur <= i1 : cur >= i1) {
-            u32 word;
-            if (w.bits != nullptr) word = w.bits[cur >> 5];
-            else {
-                const int k = ((cur >> 5) << 5) + lane;
-                word = __ballot_sync(NTL_FULL, k < w.n && wt_telo_count(w, k, wt_count(w, k < w.n ? k : 0)));
+    int need = (int)R;
+    if ((double)need < R) need += 1;                     /* in_a_row >= R for an integer in_a_row */
+    int cur = i0;
+    for (;;) {
+        const int a = next_window(w, cur, i1, dir, true, lane);
+        if (a == i1 + dir) { *first = -1; return -1; }
+        const int b = next_window(w, a + dir, i1, dir, false, lane);
+        const int len = (b - a) * dir;
+        if (len >= need) {
+            double score = 0.0;
+            for (int j0 = 0; j0 < len; j0 += 32) {
+                const int k = a + (j0 + lane) * dir;
+                double d = 0.0;
+                if (j0 + lane < len) d = wt_density_of_count(w, k, wt_count(w, k));
+                const int m = len - j0 < 32 ? len - j0 : 32;
+                for (int j = 0; j < m; j++) {
+                    score = score + __shfl_sync(NTL_FULL, d, j);                 /* :1014 */
+                    if (j0 + j + 1 >= need && score >= T) { *first = a; return a + (j0 + j) * dir; }
+                }
             }
-            int z;
-            if (dir > 0) {
-                const u32 m = word >> (cur & 31);
-                if (m == 0u) { score = 0.0; run_first = -1; in_a_row = 0; cur = ((cur >> 5) + 1) << 5; continue; }
-                z = __ffs((int)m) - 1;
-            } else {
-                const u32 m = word << (31 - (cur & 31));
-                if (m == 0u) { score = 0.0; run_first = -1; in_a_row = 0; cur = ((cur >> 5) << 5) - 1; continue; }
-                z = __clz((int)m);
-            }
-            if (z > 0) {
-                score = 0.0; run_first = -1; in_a_row = 0;
-                cur += dir * z;
-                if (dir > 0 ? cur > i1 : cur < i1) break;
-            }
-            in_a_row += 1;
-            score = score + wt_density_of_count(w, cur, wt_count(w, cur));   /* :1014 */
-            if (run_first == -1) run_first = cur;
-            if ((double)in_a_row >= R && score >= T) { *first = run_first; return cur; }
-            cur += dir;
         }
-        *first = run_first;
-        return -1;
+        if (b == i1 + dir) { *first = a; return -1; }   /* the scan ends inside this run */
+        cur = b + dir;
     }
 }
 
@@ -376,9 +396,10 @@ __device__ __noinline__ void find_telo_position(const WinTab &w, double R, doubl
     const int end_position = hit + 2;                                    /* 1-based i + 1 (:1022) */
     int end;
     if ((double)end_position >= (double)n - R + 1.0) {                   /* :1037-1044 */
-        int i = n;                                                       /* 1-based */
-        while (i > end_position && !wt_telo(w, i - 1)) i -= 1;
-        end = wt_end(w, i - 1);
+        /* i = n; while (i > end_position && window i is not telomeric) i--  (1-based): the last telomeric window
+         * among 0-based end_position .. n-1, else end_position - 1 */
+        const int j = next_window(w, n - 1, end_position, -1, true, lane);
+        end = wt_end(w, j < n - 1 ? j : n - 1);          /* end_position may be n + 1: the loop does not run */
     } else {                                                             /* :1046-1068 */
         int bfirst = -1;
         run_scan(w, n - 1, end_position - 1, -1, R, T, &bfirst, lane);
@@ -392,7 +413,7 @@ __device__ __noinline__ void find_telo_position(const WinTab &w, double R, doubl
  * edge (right = false: window 0 upward, true: window n-1 downward) to the first telomeric window, give up as soon as
  * a window lies more than max_diff = 200 from that edge, then extend over the telomeric run.  n == 0 with the right
  * edge is the caller's REF_ERROR case. */
-__device__ __noinline__ void find_edge_telo(const WinTab &w, bool right, int *ps, int *pe)
+__device__ __noinline__ void find_edge_telo(const WinTab &w, bool right, int *ps, int *pe, int lane)
 {
     const int n = w.n;
     if (!w.any) {                       /* no telomeric window anywhere: only the max_diff test can fire */
@@ -410,9 +431,10 @@ __device__ __noinline__ void find_edge_telo(const WinTab &w, bool right, int *ps
         break;
     }
     const int anchor = last_i;          /* find_left_telo keeps last_i_start (:937), find_right_telo moves last_i (:886) */
-    for (int i = last_i; i >= 0 && i < n; i += dir) {
-        if (!wt_telo(w, i)) break;
-        if (right) { start = wt_start(w, i); last_i = i; } else end = wt_end(w, i);
+    if (wt_telo(w, last_i)) {           /* extend over the run of telomeric windows that starts at last_i */
+        const int lim = right ? 0 : n - 1;
+        const int last = next_window(w, last_i, lim, dir, false, lane) - dir;
+        if (right) { start = wt_start(w, last); last_i = last; } else end = wt_end(w, last);
     }
     const int ref = right ? last_i : anchor;
     if (start > end) end = start + (wt_end(w, ref) - wt_start(w, ref));
@@ -435,8 +457,15 @@ __device__ __noinline__ int covered_in(const ReadView &rv, const WinTab &w, int 
     int total = 0, kf = klo, kl = khi;
     if (lo != wt_start(w, klo)) { total += local_count(rv, t, lo, wt_end(w, klo), lane); kf = klo + 1; }
     if (hi != wt_end(w, khi)) { total += local_count(rv, t, wt_start(w, khi), hi, lane); kl = khi - 1; }
+    /* whole windows kf .. kl: the prefixes telescope.  They are kept mod 2^16, so a difference is exact as long as
+     * its span covers fewer than 65536 bases: one span of `seg` windows per lane */
+    const int seg = 65535 / w.S;
     int part = 0;
-    for (int k = kf + lane; k <= kl; k += 32) part += wt_count(w, k);
+    for (int k0 = kf + lane * seg; k0 <= kl; k0 += 32 * seg) {
+        const int k1 = k0 + seg - 1 < kl ? k0 + seg - 1 : kl;
+        const u32 hi16 = w.cum[k1], lo16 = k0 > 0 ? (u32)w.cum[k0 - 1] : 0u;
+        part += (int)((hi16 - lo16) & 0xffffu);
+    }
     return total + (int)__reduce_add_sync(NTL_FULL, (unsigned)part);
 }
 
@@ -735,7 +764,7 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
 
 __device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *state, int lane, u32 *sbits);
 
-__global__ void __launch_bounds__(128) ntl_locate_kernel(const ntl_read_args a)
+__global__ void __launch_bounds__(128, 8) ntl_locate_kernel(const ntl_read_args a)
 {
     __shared__ u32 s_bits[4][NTL_BITS_WORDS];
     const int lane = threadIdx.x & 31;
@@ -844,8 +873,8 @@ __device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *stat
             if (te - ts + 1 < 100) {                                                       /* :1129-1136 */
                 if (c_prm.right_edge) {
                     if (w.n == 0) { err = true; break; }                                   /* R stops at :859-861 */
-                    find_edge_telo(w, true, &ts, &te);
-                } else find_edge_telo(w, false, &ts, &te);
+                    find_edge_telo(w, true, &ts, &te, lane);
+                } else find_edge_telo(w, false, &ts, &te, lane);
             }
             if (stg && lane == 0) {
                 ntl_stage s;
