@@ -32,6 +32,7 @@ cudaError_t ntl_k_filter(const ntl_read_args *a, cudaStream_t st);
 cudaError_t ntl_k_triage(const ntl_read_args *a, cudaStream_t st);
 cudaError_t ntl_k_locate(const ntl_read_args *a, int grid, cudaStream_t st);
 cudaError_t ntl_k_locate_occupancy(int *blocks_per_sm);
+cudaError_t ntl_k_gather_windows(const ntl_read_args *a, const int64_t *list, int n_list, uint16_t *dst, int T, cudaStream_t st);
 }
 
 namespace {
@@ -91,8 +92,10 @@ struct ntl_ctx {
     size_t dens_offset = 0;
     size_t meta_bytes = 0, off_len = 0, off_woff = 0, off_winoff = 0, off_order = 0, off_fmt = 0;
 
-    PinnedBuf h_packed, h_meta, h_results, h_cum, h_stages;
-    DevBuf d_packed, d_meta, d_results, d_cum, d_stages, d_pass, d_counter, d_thr, d_flags;
+    PinnedBuf h_packed, h_meta, h_results, h_cum, h_stages, h_list;
+    DevBuf d_packed, d_meta, d_results, d_cum, d_stages, d_pass, d_counter, d_thr, d_flags, d_kept, d_list;
+    std::vector<int64_t> kept_off;          /* per read: first element of its rows in h_cum, -1 = not downloaded */
+    std::vector<uint16_t> win_scratch;      /* ntl_get_windows of a read that was not kept: fetched on demand     */
     ntl_timings tm;
 };
 
@@ -121,6 +124,13 @@ double now_ms()
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
+
+/* NTL_TRACE=1: phase times of the host side on stderr (development aid) */
+struct Trace {
+    bool on; double t;
+    Trace() : on(getenv("NTL_TRACE") != nullptr), t(now_ms()) {}
+    void mark(const char *what) { if (on) { const double n = now_ms(); fprintf(stderr, "[ntl] %-22s %8.3f ms\n", what, n - t); t = n; } }
+};
 
 int32_t count_windows(int64_t L, int32_t S)
 {
@@ -351,6 +361,7 @@ extern "C" void ntl_destroy(ntl_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->jit) ntl_jit_free(c->jit);
     c->h_packed.release(); c->h_meta.release(); c->h_results.release(); c->h_cum.release(); c->h_stages.release();
+    c->h_list.release(); c->d_kept.release(); c->d_list.release();
     c->d_packed.release(); c->d_meta.release(); c->d_results.release(); c->d_cum.release(); c->d_stages.release();
     c->d_pass.release(); c->d_counter.release(); c->d_thr.release(); c->d_flags.release();
     for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -375,7 +386,7 @@ static int ensure_device_buffers(ntl_ctx *c, int64_t packed_words)
     return NTL_OK;
 }
 
-/* overlap = true: the packed words are copied to the device in 16 MiB pieces while the remaining reads are still
+/* overlap = true: the packed words are copied to the device in 8 MiB pieces while the remaining reads are still
  * being packed (the calling thread issues the copies between its own grains), so that PCIe time hides behind the
  * packer; the batch ends up in state UPLOADED. */
 static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len, int32_t n, bool overlap)
@@ -384,6 +395,7 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
     if (!seq || !len || n < 0) return fail(c, NTL_ERR_ARG, "ntl_batch_pack: bad arguments");
     CK(c, cudaSetDevice(c->device));
     const double t0 = now_ms();
+    Trace tr;
     c->state = ST_EMPTY;
     c->n_reads = n;
     const int32_t S = c->dev.S;
@@ -420,11 +432,35 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
         wins += ((int64_t)count_windows(L, S) + 7) & ~(int64_t)7;   /* each read starts on a 16-byte boundary of the uint16 planes */
         bases += L;
     }
+    tr.mark("tables");
     const int64_t main_words = words;
     c->total_windows = wins;
     c->bases = bases;
     CK(c, c->h_packed.ensure((size_t)main_words * 4 + 64));
     uint32_t *hp = (uint32_t *)c->h_packed.p;
+
+    /* ---- work order: longest reads first (by 4096-position steps), 2-bit reads then 4-bit reads */
+    auto work_order = [&]() {
+        int32_t maxc = 0;
+        std::vector<int32_t> chunks(n);
+        for (int32_t i = 0; i < n; i++) {
+            const int64_t nq = ((((int64_t)h_len[i] >> 5) + 1) + 3) >> 2;
+            chunks[i] = (int32_t)((nq + 31) >> 5);
+            if (chunks[i] > maxc) maxc = chunks[i];
+        }
+        std::vector<int64_t> cnt2((size_t)maxc + 2, 0), cnt4((size_t)maxc + 2, 0);
+        int32_t n2 = 0, n4 = 0;
+        for (int32_t i = 0; i < n; i++) { if (h_fmt[i]) { cnt4[chunks[i]]++; n4++; } else { cnt2[chunks[i]]++; n2++; } }
+        /* descending: position of bucket k = number of reads with more chunks */
+        std::vector<int64_t> pos2((size_t)maxc + 2, 0), pos4((size_t)maxc + 2, 0);
+        int64_t a2 = 0, a4 = 0;
+        for (int32_t k = maxc; k >= 0; k--) { pos2[k] = a2; a2 += cnt2[k]; pos4[k] = a4; a4 += cnt4[k]; }
+        for (int32_t i = 0; i < n; i++) {
+            if (h_fmt[i]) h_order[n2 + pos4[chunks[i]]++] = i;
+            else h_order[pos2[chunks[i]]++] = i;
+        }
+        c->n2 = n2; c->n4 = n4;
+    };
 
     /* ---- 2-bit packing, all host threads; reads with other letters are queued for the 4-bit arena */
     std::vector<int32_t> iupac;
@@ -446,7 +482,7 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
         if (rc0 != NTL_OK) return rc0;
         CK(c, cudaEventRecord(c->ev[0], c->stream));
         const int64_t grain = 64, ngr = (n + grain - 1) / grain;
-        const int64_t piece = 4 << 20;          /* 16 MiB */
+        const int64_t piece = 2 << 20;          /* 8 MiB */
         std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[(size_t)ngr + 1]);
         for (int64_t g = 0; g <= ngr; g++) done[g].store(0, std::memory_order_relaxed);
         std::atomic<int64_t> next(0);
@@ -463,7 +499,8 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
         };
         std::vector<std::thread> th;
         for (int t = 1; t < c->host_threads && t < ngr; t++) th.emplace_back(worker);
-        cudaError_t cerr = cudaSuccess;
+        work_order();                           /* h_fmt is all zero here; redone below if a read needs 4 bits */
+        cudaError_t cerr = cudaMemcpyAsync(c->d_meta.p, c->h_meta.p, c->meta_bytes, cudaMemcpyHostToDevice, c->stream);
         int64_t uf = 0;
         for (;;) {
             while (uf < ngr && done[uf].load(std::memory_order_acquire)) uf++;
@@ -481,6 +518,7 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
         for (auto &t : th) t.join();
         if (cerr != cudaSuccess) return fail(c, NTL_ERR_CUDA, "cudaMemcpyAsync (packed reads) failed: %s", cudaGetErrorString(cerr));
     }
+    tr.mark("pack 2-bit (+copies)");
     if (!iupac.empty()) {
         std::sort(iupac.begin(), iupac.end());
         std::vector<int64_t> aoff(iupac.size());
@@ -503,29 +541,12 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
         if (bad >= 0) return fail(c, NTL_ERR_SEQUENCE, "read %d holds a letter outside the DNA alphabet", bad);
     }
     c->total_words = words;
+    tr.mark("pack 4-bit");
 
-    /* ---- work order: longest reads first (by 4096-position steps), 2-bit reads then 4-bit reads */
-    {
-        int32_t maxc = 0;
-        std::vector<int32_t> chunks(n);
-        for (int32_t i = 0; i < n; i++) {
-            const int64_t nq = ((((int64_t)h_len[i] >> 5) + 1) + 3) >> 2;
-            chunks[i] = (int32_t)((nq + 31) >> 5);
-            if (chunks[i] > maxc) maxc = chunks[i];
-        }
-        std::vector<int64_t> cnt2((size_t)maxc + 2, 0), cnt4((size_t)maxc + 2, 0);
-        int32_t n2 = 0, n4 = 0;
-        for (int32_t i = 0; i < n; i++) { if (h_fmt[i]) { cnt4[chunks[i]]++; n4++; } else { cnt2[chunks[i]]++; n2++; } }
-        /* descending: position of bucket k = number of reads with more chunks */
-        std::vector<int64_t> pos2((size_t)maxc + 2, 0), pos4((size_t)maxc + 2, 0);
-        int64_t a2 = 0, a4 = 0;
-        for (int32_t k = maxc; k >= 0; k--) { pos2[k] = a2; a2 += cnt2[k]; pos4[k] = a4; a4 += cnt4[k]; }
-        for (int32_t i = 0; i < n; i++) {
-            if (h_fmt[i]) h_order[n2 + pos4[chunks[i]]++] = i;
-            else h_order[pos2[chunks[i]]++] = i;
-        }
-        c->n2 = n2; c->n4 = n4;
-    }
+    /* overlap mode built the order and sent the tables while the workers were packing, assuming 2-bit reads only */
+    const bool tables_sent = overlap && iupac.empty();
+    if (!tables_sent) work_order();
+    tr.mark("work order");
     c->tm = ntl_timings();
     c->tm.pack_ms = now_ms() - t0;
     c->tm.bases = bases;
@@ -541,7 +562,7 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
         if (words > up_words)
             CK(c, cudaMemcpyAsync((uint32_t *)c->d_packed.p + up_words, (uint32_t *)c->h_packed.p + up_words,
                                   (size_t)(words - up_words) * 4, cudaMemcpyHostToDevice, c->stream));
-        if (c->meta_bytes > 0)
+        if (c->meta_bytes > 0 && !tables_sent)
             CK(c, cudaMemcpyAsync(c->d_meta.p, c->h_meta.p, c->meta_bytes, cudaMemcpyHostToDevice, c->stream));
         CK(c, cudaEventRecord(c->ev[1], c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
@@ -550,6 +571,7 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
         c->tm.h2d_ms = ms;                       /* first copy issued -> last copy done; overlaps pack_ms */
         c->tm.h2d_bytes = words * 4 + (int64_t)c->meta_bytes;
         c->tm.pack_ms = now_ms() - t0;
+        tr.mark("tail copies + sync");
         c->state = ST_UPLOADED;
     }
     return NTL_OK;
@@ -582,22 +604,11 @@ extern "C" int ntl_batch_upload(ntl_ctx *c)
     return NTL_OK;
 }
 
-/* ============================================================================================== run */
-/* Enqueue one pass of the hot path (filter, scan, locate) on the context stream without waiting.  Event quads live
- * in a ring so that a timed loop of back-to-back passes still yields per-kernel device times. */
-extern "C" int ntl_batch_enqueue(ntl_ctx *c)
+static void fill_read_args(const ntl_ctx *c, ntl_read_args *out)
 {
-    if (!c) return NTL_ERR_ARG;
-    if (c->state < ST_UPLOADED) return fail(c, NTL_ERR_STATE, "ntl_batch_enqueue before ntl_batch_upload");
-    CK(c, cudaSetDevice(c->device));
-    if (c->pending >= NTL_EVENT_RING) return fail(c, NTL_ERR_STATE, "more than %d passes enqueued without ntl_batch_wait", NTL_EVENT_RING);
     const int32_t n = c->n_reads;
     const int T = c->dev.n_tracks;
     char *dm = (char *)c->d_meta.p;
-    cudaEvent_t *ev = c->ring[c->pending];
-    for (int i = 0; i < 4; i++)
-        if (!ev[i]) CK(c, cudaEventCreate(&ev[i]));
-
     ntl_read_args ra;
     memset(&ra, 0, sizeof ra);
     ra.packed = (const uint32_t *)c->d_packed.p;
@@ -616,6 +627,27 @@ extern "C" int ntl_batch_enqueue(ntl_ctx *c)
     ra.counters = (uint32_t *)c->d_counter.p + 4;
     ra.stages = c->dev.debug_stages ? c->d_stages.p : nullptr;
     ra.n_reads = n;
+    *out = ra;
+}
+
+/* ============================================================================================== run */
+/* Enqueue one pass of the hot path (filter, scan, locate) on the context stream without waiting.  Event quads live
+ * in a ring so that a timed loop of back-to-back passes still yields per-kernel device times. */
+extern "C" int ntl_batch_enqueue(ntl_ctx *c)
+{
+    if (!c) return NTL_ERR_ARG;
+    if (c->state < ST_UPLOADED) return fail(c, NTL_ERR_STATE, "ntl_batch_enqueue before ntl_batch_upload");
+    CK(c, cudaSetDevice(c->device));
+    if (c->pending >= NTL_EVENT_RING) return fail(c, NTL_ERR_STATE, "more than %d passes enqueued without ntl_batch_wait", NTL_EVENT_RING);
+    const int32_t n = c->n_reads;
+    const int T = c->dev.n_tracks;
+    char *dm = (char *)c->d_meta.p;
+    cudaEvent_t *ev = c->ring[c->pending];
+    for (int i = 0; i < 4; i++)
+        if (!ev[i]) CK(c, cudaEventCreate(&ev[i]));
+
+    ntl_read_args ra;
+    fill_read_args(c, &ra);
 
     ntl_scan_args sa;
     memset(&sa, 0, sizeof sa);
@@ -693,6 +725,10 @@ extern "C" int ntl_batch_run(ntl_ctx *c)
 }
 
 /* ============================================================================================== download */
+/* Results come back in two steps: the 64-byte records (and the debug stages) first; then, for the reads the keep rule
+ * retained -- the only ones whose window tables the caller needs (NanoTel.R:1876-1918) -- the window prefixes, gathered
+ * on the device into one contiguous block.  The tables of all other reads stay on the device until the next batch
+ * and are fetched on demand by ntl_get_windows(). */
 extern "C" int ntl_batch_download(ntl_ctx *c, const ntl_read_result **results)
 {
     if (!c) return NTL_ERR_ARG;
@@ -701,23 +737,45 @@ extern "C" int ntl_batch_download(ntl_ctx *c, const ntl_read_result **results)
     const int32_t n = c->n_reads;
     const int T = c->dev.n_tracks;
     const size_t rbytes = (size_t)n * sizeof(ntl_read_result);
-    const size_t cbytes = (size_t)c->total_windows * 2 * T;
     const size_t sbytes = c->dev.debug_stages ? (size_t)n * 3 * sizeof(ntl_stage) : 0;
     CK(c, c->h_results.ensure(rbytes + 64));
-    CK(c, c->h_cum.ensure(cbytes + 64));
     if (sbytes) CK(c, c->h_stages.ensure(sbytes + 64));
     CK(c, cudaEventRecord(c->ev[6], c->stream));
     if (rbytes) CK(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, rbytes, cudaMemcpyDeviceToHost, c->stream));
-    if (cbytes) CK(c, cudaMemcpyAsync(c->h_cum.p, c->d_cum.p, cbytes, cudaMemcpyDeviceToHost, c->stream));
     if (sbytes) CK(c, cudaMemcpyAsync(c->h_stages.p, c->d_stages.p, sbytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+
+    const ntl_read_result *res = (const ntl_read_result *)c->h_results.p;
+    c->kept_off.assign((size_t)n, -1);
+    int64_t n_kept = 0, elems = 0;
+    for (int32_t i = 0; i < n; i++) n_kept += (res[i].status & NTL_READ_KEEP) ? 1 : 0;
+    if (n_kept > 0) {
+        CK(c, c->h_list.ensure((size_t)n_kept * 16));
+        int64_t *list = (int64_t *)c->h_list.p;
+        int64_t k = 0;
+        for (int32_t i = 0; i < n; i++) {
+            if (!(res[i].status & NTL_READ_KEEP)) continue;
+            list[2 * k] = i; list[2 * k + 1] = elems; k++;
+            c->kept_off[(size_t)i] = elems;
+            elems += (((int64_t)res[i].n_win + 7) & ~(int64_t)7) * T;
+        }
+        CK(c, c->d_list.ensure((size_t)n_kept * 16));
+        CK(c, c->d_kept.ensure((size_t)elems * 2 + 64));
+        CK(c, c->h_cum.ensure((size_t)elems * 2 + 64));
+        CK(c, cudaMemcpyAsync(c->d_list.p, list, (size_t)n_kept * 16, cudaMemcpyHostToDevice, c->stream));
+        ntl_read_args ra;
+        fill_read_args(c, &ra);
+        CK(c, ntl_k_gather_windows(&ra, (const int64_t *)c->d_list.p, (int)n_kept, (uint16_t *)c->d_kept.p, T, c->stream));
+        CK(c, cudaMemcpyAsync(c->h_cum.p, c->d_kept.p, (size_t)elems * 2, cudaMemcpyDeviceToHost, c->stream));
+    }
     CK(c, cudaEventRecord(c->ev[7], c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     CK(c, cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]));
     c->tm.d2h_ms = ms;
-    c->tm.d2h_bytes = (int64_t)(rbytes + cbytes + sbytes);
+    c->tm.d2h_bytes = (int64_t)(rbytes + (size_t)elems * 2 + sbytes);
     c->state = ST_DOWNLOADED;
-    if (results) *results = (const ntl_read_result *)c->h_results.p;
+    if (results) *results = res;
     return NTL_OK;
 }
 
@@ -726,9 +784,13 @@ extern "C" int ntl_scan_batch(ntl_ctx *c, const char *const *seq, const int64_t 
 {
     if (!c) return NTL_ERR_ARG;
     const double t0 = now_ms();
+    Trace tr;
     int rc = pack_internal(c, seq, len, n, /*overlap=*/true);
+    tr.mark("pack_internal");
     if (rc == NTL_OK) rc = ntl_batch_run(c);
+    tr.mark("run");
     if (rc == NTL_OK) rc = ntl_batch_download(c, results);
+    tr.mark("download");
     c->tm.total_ms = now_ms() - t0;
     return rc;
 }
@@ -766,7 +828,18 @@ extern "C" int ntl_get_windows(const ntl_ctx *c, int32_t read_idx, int32_t track
     if (r->status & NTL_READ_FILTERED) return 0;
     const int32_t n = r->n_win, S = c->dev.S;
     const int32_t L = ((const int32_t *)((const char *)c->h_meta.p + c->off_len))[read_idx];
-    const uint16_t *cum = (const uint16_t *)c->h_cum.p + (size_t)track * c->total_windows + r->win_offset;
+    const uint16_t *cum;
+    if (c->kept_off[(size_t)read_idx] >= 0) {
+        cum = (const uint16_t *)c->h_cum.p + c->kept_off[(size_t)read_idx] + (size_t)track * (((size_t)n + 7) & ~(size_t)7);
+    } else {                                    /* not a kept read: its table is still on the device */
+        if (cudaSetDevice(c->device) != cudaSuccess) return fail(mc, NTL_ERR_CUDA, "cudaSetDevice failed");
+        mc->win_scratch.resize((size_t)n + 8);
+        const uint16_t *src = (const uint16_t *)c->d_cum.p + (size_t)track * c->total_windows + r->win_offset;
+        cudaError_t e = cudaMemcpyAsync(mc->win_scratch.data(), src, (size_t)n * 2, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return fail(mc, NTL_ERR_CUDA, "ntl_get_windows: %s", cudaGetErrorString(e));
+        cum = mc->win_scratch.data();
+    }
     for (int32_t k = 0; k < n && k < cap; k++) {
         const int32_t ws = 1 + k * S, we = (k == n - 1) ? L : (k + 1) * S;
         const int32_t cnt = (int32_t)((uint32_t)(cum[k] - (k ? cum[k - 1] : 0)) & 0xffffu);

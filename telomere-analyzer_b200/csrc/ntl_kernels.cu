@@ -955,6 +955,31 @@ extern "C" cudaError_t ntl_k_locate(const ntl_read_args *a, int grid, cudaStream
     return cudaGetLastError();
 }
 
+/* Window prefixes of the kept reads only, packed for the device-to-host copy: entry i of `list` = {read, first
+ * destination element}; a read's T rows of pw = n_win rounded up to 8 elements follow each other.  One warp per
+ * entry, 16-byte moves (source and destination rows start on multiples of 8 elements). */
+__global__ void __launch_bounds__(128) ntl_gather_windows_kernel(const ntl_read_args a, const int64_t *list, int n_list,
+                                                                 uint16_t *dst, int T)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_list) return;
+    const int r = (int)list[2 * i];
+    const int groups = (ntl_nwin(a.len[r], c_prm.S) + 7) >> 3;
+    for (int t = 0; t < T; t++) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.cum[t] + a.win_off[r]);
+        uint4 *out = reinterpret_cast<uint4 *>(dst + list[2 * i + 1]) + (size_t)t * groups;
+        for (int g = lane; g < groups; g += 32) out[g] = __ldg(src + g);
+    }
+}
+
+extern "C" cudaError_t ntl_k_gather_windows(const ntl_read_args *a, const int64_t *list, int n_list, uint16_t *dst, int T,
+                                            cudaStream_t st)
+{
+    if (n_list <= 0) return cudaSuccess;
+    ntl_gather_windows_kernel<<<(n_list * 32 + 127) / 128, 128, 0, st>>>(*a, list, n_list, dst, T);
+    return cudaGetLastError();
+}
+
 extern "C" cudaError_t ntl_k_locate_occupancy(int *blocks_per_sm)
 {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ntl_locate_kernel, 128, 0);

@@ -80,21 +80,29 @@ class Scanner:
         lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=n)
         return arr, lens
 
-    def _results_view(self, ptr: C.c_void_p, n: int) -> np.ndarray:
+    def _results_view(self, ptr: C.c_void_p, n: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """The records of the last batch, copied out of the context's pinned buffer (which the next batch reuses):
+        into `out` (RESULT_DTYPE, >= n entries, no allocation and no page faults) or into a fresh array."""
         if n == 0:
             return np.zeros(0, _lib.RESULT_DTYPE)
         buf = (C.c_char * (n * 64)).from_address(ptr.value)
-        # one flat memcpy out of the context's pinned buffer (a structured-dtype .copy() is ~10x slower)
-        return np.frombuffer(buf, dtype=np.uint8, count=n * 64).copy().view(_lib.RESULT_DTYPE)
+        # one flat memcpy (a structured-dtype .copy() is ~10x slower)
+        src = np.frombuffer(buf, dtype=np.uint8, count=n * 64)
+        if out is None:
+            return src.copy().view(_lib.RESULT_DTYPE)
+        if out.dtype != _lib.RESULT_DTYPE or out.ndim != 1 or out.shape[0] < n or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous 1-d RESULT_DTYPE array with at least %d entries" % n)
+        np.copyto(out[:n].view(np.uint8), src)
+        return out[:n]
 
-    def scan(self, seqs: Sequence[bytes]) -> np.ndarray:
+    def scan(self, seqs: Sequence[bytes], out: Optional[np.ndarray] = None) -> np.ndarray:
         """ntl_scan_batch: host ASCII reads in, one RESULT_DTYPE record per read out (a copy)."""
         arr, lens = self._marshal(seqs)
         self._keep = (arr, lens, seqs)
-        out = C.c_void_p()
-        self._check(self._L.ntl_scan_batch(self._h, arr, lens.ctypes.data, len(seqs), C.byref(out)))
+        res = C.c_void_p()
+        self._check(self._L.ntl_scan_batch(self._h, arr, lens.ctypes.data, len(seqs), C.byref(res)))
         self._n = len(seqs)
-        return self._results_view(out, self._n)
+        return self._results_view(res, self._n, out)
 
     @staticmethod
     def _marshal_concat(buf: np.ndarray, offsets: np.ndarray):
@@ -104,14 +112,16 @@ class Scanner:
         lens = np.diff(offsets).astype(np.int64)
         return buf, ptrs, lens
 
-    def scan_concat(self, buf: np.ndarray, offsets: np.ndarray) -> np.ndarray:
-        """Reads given as one ASCII buffer + offsets (read i = buf[offsets[i]:offsets[i+1]])."""
-        buf, ptrs, lens = self._marshal_concat(buf, offsets)
-        self._keep = (buf, ptrs, lens)
-        out = C.c_void_p()
-        self._check(self._L.ntl_scan_batch(self._h, ptrs.ctypes.data, lens.ctypes.data, len(lens), C.byref(out)))
-        self._n = len(lens)
-        return self._results_view(out, self._n)
+    def scan_concat(self, buf: np.ndarray, offsets: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """ntl_scan_batch_concat: reads given as one ASCII buffer + offsets (read i = buf[offsets[i]:offsets[i+1]])."""
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._keep = (buf, offsets)
+        n = len(offsets) - 1
+        res = C.c_void_p()
+        self._check(self._L.ntl_scan_batch_concat(self._h, buf.ctypes.data, offsets.ctypes.data, n, C.byref(res)))
+        self._n = n
+        return self._results_view(res, n, out)
 
     def pack_concat(self, buf: np.ndarray, offsets: np.ndarray) -> None:
         buf, ptrs, lens = self._marshal_concat(buf, offsets)
@@ -137,10 +147,10 @@ class Scanner:
     def wait(self) -> None:
         self._check(self._L.ntl_batch_wait(self._h))
 
-    def download(self) -> np.ndarray:
-        out = C.c_void_p()
-        self._check(self._L.ntl_batch_download(self._h, C.byref(out)))
-        return self._results_view(out, self._n)
+    def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        res = C.c_void_p()
+        self._check(self._L.ntl_batch_download(self._h, C.byref(res)))
+        return self._results_view(res, self._n, out)
 
     def timings(self) -> dict:
         t = _lib.Timings()

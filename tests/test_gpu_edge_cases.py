@@ -70,3 +70,34 @@ def test_call_order_is_checked():
         sc.upload(); sc.run()
         res = sc.download()
         assert res[0]["status"] & 1
+
+
+def test_only_kept_reads_send_their_window_tables_to_the_host():
+    """ntl_batch_download moves the 64-byte records and the window prefixes of the kept reads; the table of any other
+    read is fetched from the device when ntl_get_windows asks for it.  Both routes must give the same table as a
+    context that holds only that read.  `out=` receives the records without an allocation."""
+    from nanotel_b200 import RESULT_DTYPE, Scanner
+    rng = np.random.default_rng(77)
+    seqs = []
+    for i in range(60):
+        L = int(rng.integers(1500, 9000))
+        seqs.append(_long_read(rng, L, bool(i % 3 == 0), 1200) if i % 2 == 0 else bytes(rng.choice(ACGT, L)))
+    out = np.empty(len(seqs) + 5, RESULT_DTYPE)
+    with Scanner("TTAGGG", "TTGGG") as sc:
+        res = sc.scan(seqs, out=out)
+        assert np.shares_memory(res, out) and len(res) == len(seqs)
+        assert res.tobytes() == sc.scan(seqs).tobytes()
+        tm = sc.timings()
+        kept = np.flatnonzero(res["status"] & 1)
+        assert 0 < len(kept) < len(seqs)
+        rows = sum(((int(res[i]["n_win"]) + 7) & ~7) for i in kept)
+        assert tm["d2h_bytes"] == 64 * len(seqs) + rows * 2 * sc.n_tracks
+        tables = {(i, t): sc.windows(i, t) for i in range(len(seqs)) for t in range(sc.n_tracks)}
+        with pytest.raises(ValueError):
+            sc.scan(seqs, out=np.empty(3, RESULT_DTYPE))
+    with Scanner("TTAGGG", "TTGGG") as one:
+        for i in list(kept[:4]) + [j for j in range(len(seqs)) if j not in set(kept)][:4]:
+            one.scan([seqs[i]])
+            for t in range(one.n_tracks):
+                for a, b in zip(tables[(i, t)], one.windows(0, t)):
+                    assert np.array_equal(a, b), (i, t)
