@@ -103,7 +103,8 @@ typedef struct {        /* wall/device times of the last batch, milliseconds */
     double h2d_ms;          /* device: packed reads + tables upload (CUDA events)                            */
     double filter_ms;       /* device: edge-filter kernel                                                    */
     double scan_ms;         /* device: match + coverage + window-prefix kernel(s)  (the dominant kernel)     */
-    double locate_ms;       /* device: per-read locator / refinement kernel                                  */
+    double locate_ms;       /* device: triage + per-read locator / refinement kernels                        */
+    double triage_ms;       /* device: the triage kernel alone, FIRST pass only (not a sum; part of locate_ms) */
     double d2h_ms;          /* device: results + window prefixes download                                    */
     double total_ms;        /* host wall clock of the whole ntl_scan_batch call                              */
     int64_t bases;          /* bases in the batch                                                            */
@@ -141,13 +142,17 @@ int ntl_batch_upload(ntl_ctx *ctx);       /* pinned host -> HBM (async on the co
 int ntl_batch_run(ntl_ctx *ctx);          /* filter + scan + locate kernels on the resident batch, sync    */
 int ntl_batch_enqueue(ntl_ctx *ctx);      /* the same pass, enqueued on the context stream without waiting  */
 int ntl_batch_wait(ntl_ctx *ctx);         /* wait for the enqueued passes (<= 256); timings = sums over them */
+/* HBM -> pinned host: the 64-byte records of all reads, then the window tables of the reads with NTL_READ_KEEP (the
+ * only ones analyze_read plots, NanoTel.R:1876-1918), gathered on the device into one block.                      */
 int ntl_batch_download(ntl_ctx *ctx, const ntl_read_result **results);
 int ntl_get_timings(const ntl_ctx *ctx, ntl_timings *out);
 void *ntl_stream(const ntl_ctx *ctx);     /* cudaStream_t the kernels are launched on */
 
 /* -- per-window tables of the last batch (the data.frames analyze_subtelos returns, NanoTel.R:740-765) ------- */
 /* Fills up to cap rows for read read_idx, track (0..2): start_index, end_index, covered bases and
- * density = covered / width (the plot vectors).  Any output pointer may be NULL.  Returns n_win or < 0. */
+ * density = covered / width (the plot vectors).  Any output pointer may be NULL.  Returns n_win or < 0.
+ * Kept reads are served from the host copy; the table of any other read is still on the device and is fetched by
+ * this call (one small synchronous copy), until the next batch replaces it. */
 int ntl_get_windows(const ntl_ctx *ctx, int32_t read_idx, int32_t track, int32_t cap,
                     int32_t *start_index, int32_t *end_index, int32_t *covered, double *density);
 /* NTL_OPT_DEBUG_STAGES only: intermediate intervals of read read_idx, track. */

@@ -671,10 +671,11 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
                 /* any window with  !(count / width < min_density)  on any track?  Every read's window range starts
                  * on a multiple of 8 entries, so groups of 8 prefixes are 16-byte aligned. */
                 const int thr_reg = c_prm.thr_reg;
+                const u32 thr16 = (u32)thr_reg << 16;
                 const int thr_last = (int)a.thr[L - (n_win - 1) * S];
                 bool tel = false;
                 const int full = (n_win - 1) >> 3;               /* groups made of width-S windows only */
-                u32 carry[3] = {0u, 0u, 0u};                     /* last prefix of the previous step */
+                u32 carry[3] = {0u, 0u, 0u};                     /* last word of the previous step */
                 for (int g0 = 0; g0 < full; g0 += 8) {
                     const int g = g0 + sub;
                     uint4 v[3];
@@ -685,18 +686,21 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
 #pragma unroll
                     for (int t = 0; t < 3; t++) {
                         if (t < T) {
-                            const u32 last = v[t].w >> 16;
-                            u32 prev = __shfl_up_sync(tmask, last, 1, 8);
+                            u32 prev = __shfl_up_sync(tmask, v[t].w, 1, 8);
                             if (sub == 0) prev = carry[t];
-                            carry[t] = __shfl_sync(tmask, last, 7, 8);
+                            carry[t] = __shfl_sync(tmask, v[t].w, 7, 8);
                             if (g < full) {
+                                /* counts are differences of 16-bit prefixes mod 2^16: kept in the upper half of a
+                                 * word ((x << 16) drops the other prefix, the wrap is the 32-bit wrap), so a window
+                                 * costs one subtraction and one unsigned compare */
                                 const u32 x[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+                                u32 ph = prev & 0xffff0000u;
 #pragma unroll
                                 for (int q = 0; q < 4; q++) {
-                                    const u32 l16 = x[q] & 0xffffu, h16 = x[q] >> 16;
-                                    tel |= (int)((l16 - prev) & 0xffffu) >= thr_reg;
-                                    tel |= (int)((h16 - l16) & 0xffffu) >= thr_reg;
-                                    prev = h16;
+                                    const u32 xl = x[q] << 16, xh = x[q] & 0xffff0000u;
+                                    tel |= xl - ph >= thr16;
+                                    tel |= xh - xl >= thr16;
+                                    ph = xh;
                                 }
                             }
                         }
@@ -723,7 +727,7 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
         }
         if (!cand) {
             /* the 64-byte record goes out as four 16-byte stores from lanes 0..3 of the team */
-            ntl_read_result o;
+            alignas(16) ntl_read_result o;       /* stored below as four 16-byte pieces */
             o.status = status;
             o.n_win = n_win > 0 ? n_win : 0;
             for (int t = 0; t < 3; t++) {
@@ -790,21 +794,28 @@ __device__ __noinline__ bool warp_any_telomeric(const WinTab &w, int lane, u32 *
      * lane l of a step holds windows 8 l' .. 8 l' + 7, four lanes make one 32-bit word */
     const uint4 *cv = reinterpret_cast<const uint4 *>(w.cum);
     const int groups = (w.n + 7) >> 3;
+    const u32 thr16 = (u32)w.thr_reg << 16;
     bool tel = false;
     for (int g0 = 0; g0 < groups; g0 += 32) {
         const int g = g0 + lane;
         u32 b8 = 0u;
         if (g < groups) {
+            /* 16-bit differences in the upper half of a word, as in the triage kernel; every window is first held
+             * against the width-S threshold, then the read's last window (own width) and the padding are redone */
             const uint4 v = __ldg(cv + g);
             const u32 x[4] = {v.x, v.y, v.z, v.w};
-            u32 prev = g > 0 ? (u32)w.cum[8 * g - 1] : 0u;
+            u32 ph = g > 0 ? (u32)w.cum[8 * g - 1] << 16 : 0u;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const int k = 8 * g + 2 * q;
-                const u32 l16 = x[q] & 0xffffu, h16 = x[q] >> 16;
-                if (k < w.n && wt_telo_count(w, k, (int)((l16 - prev) & 0xffffu))) b8 |= 1u << (2 * q);
-                if (k + 1 < w.n && wt_telo_count(w, k + 1, (int)((h16 - l16) & 0xffffu))) b8 |= 2u << (2 * q);
-                prev = h16;
+                const u32 xl = x[q] << 16, xh = x[q] & 0xffff0000u;
+                if (xl - ph >= thr16) b8 |= 1u << (2 * q);
+                if (xh - xl >= thr16) b8 |= 2u << (2 * q);
+                ph = xh;
+            }
+            const int kl = w.n - 1 - 8 * g;
+            if (kl < 8) {
+                b8 &= (1u << kl) - 1u;
+                if (wt_telo_count(w, w.n - 1, wt_count(w, w.n - 1))) b8 |= 1u << kl;
             }
         }
         tel |= b8 != 0u;

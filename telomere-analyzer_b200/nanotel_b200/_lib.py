@@ -34,7 +34,7 @@ class Params(C.Structure):
 class Timings(C.Structure):
     _fields_ = [
         ("pack_ms", C.c_double), ("h2d_ms", C.c_double), ("filter_ms", C.c_double), ("scan_ms", C.c_double),
-        ("locate_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
+        ("locate_ms", C.c_double), ("triage_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
         ("bases", C.c_int64), ("packed_bytes", C.c_int64), ("window_bytes", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("kernel_launches", C.c_int32), ("scan_is_jit", C.c_int32), ("steps", C.c_int32), ("candidates", C.c_int32),

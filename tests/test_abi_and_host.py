@@ -32,7 +32,7 @@ def test_struct_layouts():
     _l, L = _lib()
     assert _l.RESULT_DTYPE.itemsize == 64
     assert C.sizeof(_l.Stage) == 32
-    assert C.sizeof(_l.Timings) == 7 * 8 + 5 * 8 + 4 * 4
+    assert C.sizeof(_l.Timings) == 8 * 8 + 5 * 8 + 4 * 4
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -22,4 +22,6 @@ sc.upload()
 for _ in range(a.runs):
     sc.run()
 t = sc.timings()
-print("scan_ms %.4f locate_ms %.4f candidates %d jit %d" % (t["scan_ms"], t["locate_ms"], t["candidates"], t["scan_is_jit"]))
+k = max(t["steps"], 1)
+print("scan_ms %.4f triage_ms %.4f locate_ms %.4f (triage + locate) candidates %d jit %d" % (
+    t["scan_ms"] / k, t["triage_ms"], t["locate_ms"] / k, t["candidates"], t["scan_is_jit"]))
