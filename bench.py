@@ -142,7 +142,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=100000, help="reads per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample", type=int, default=20000, help="reads of the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=50000, help="reads of the CPU-baseline sample")
     ap.add_argument("--no-jit", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -193,6 +193,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: libnanotel_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL writes its banner / debug lines to stdout by default; stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from nanotel_b200 import RESULT_DTYPE, Scanner
