@@ -268,31 +268,24 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
         const u32 g = lane >= (1 << k) ? 1u : 0u;
         asm("mov.u32 %0, %1;" : "=r"(ge[k]) : "r"(g));
     }
-    u32 cur[QW], nxt[QW];
+    /* Two quad buffers that swap roles every step: while step c works on one (chunk c), the other already holds
+     * chunk c + 1 (its first word is lane 31's fifth word), and as soon as the letter masks of chunk c are formed its
+     * registers receive chunk c + 2.  Every load is issued more than a full step before its first use, and no
+     * register is copied.  Quads beyond the read are not loaded: stale bits there are masked by v[]. */
+    u32 bufA[QW], bufB[QW];
 #pragma unroll
-    for (int i = 0; i < QW; i++) cur[i] = 0u;
-    if (lane < n_quads) {
-        if constexpr (NPL == 2) ntl_ldg256(base + (size_t)lane * 8, *reinterpret_cast<u32(*)[8]>(&cur[0]));
+    for (int i = 0; i < QW; i++) { bufA[i] = 0u; bufB[i] = 0u; }
+    auto load_quad = [&](u32 (&X)[QW], const u32 *src) {
+        if constexpr (NPL == 2) ntl_ldg256(src, *reinterpret_cast<u32(*)[8]>(&X[0]));
         else {
-            ntl_ldg256(base + (size_t)lane * 16, *reinterpret_cast<u32(*)[8]>(&cur[0]));
-            ntl_ldg256(base + (size_t)lane * 16 + 8, *reinterpret_cast<u32(*)[8]>(&cur[8]));
+            ntl_ldg256(src, *reinterpret_cast<u32(*)[8]>(&X[0]));
+            ntl_ldg256(src + 8, *reinterpret_cast<u32(*)[8]>(&X[8]));
         }
-    }
+    };
+    if (lane < n_quads) load_quad(bufA, qp);
+    if (lane + 32 < n_quads) load_quad(bufB, qp + 32 * QW);
 
-    for (int c = 0; c < n_chunks; c++) {
-        /* ---- prefetch the next chunk's quad */
-        const int qn = (c + 1) * 32 + lane;
-        qp += 32 * QW;                                         /* this lane's quad of the next chunk */
-#pragma unroll
-        for (int i = 0; i < QW; i++) nxt[i] = 0u;
-        if (qn < n_quads) {
-            if constexpr (NPL == 2) ntl_ldg256(qp, *reinterpret_cast<u32(*)[8]>(&nxt[0]));
-            else {
-                ntl_ldg256(qp, *reinterpret_cast<u32(*)[8]>(&nxt[0]));
-                ntl_ldg256(qp + 8, *reinterpret_cast<u32(*)[8]>(&nxt[8]));
-            }
-        }
-
+    auto step = [&](u32 (&cur)[QW], u32 (&nxt)[QW], const int c) {
         /* ---- planes: 4 own words + the first word of the next lane (next chunk for lane 31) */
         u32 pl[NPL][5];
 #pragma unroll
@@ -361,6 +354,10 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
 #pragma unroll
             for (int i = 0; i < 5; i++) cov[2][i] |= cov[1][i];
         }
+
+        /* ---- the planes of this chunk are dead: their registers take chunk c + 2 */
+        qp += 32 * QW;
+        if ((c + 2) * 32 + lane < n_quads) load_quad(cur, qp + 32 * QW);
 
         /* ---- coverage spill from the previous lane, trim to [1, L], popcounts */
         u32 pc[3][4], tot[3];
@@ -460,8 +457,12 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
             for (int t = 0; t < 3; t++) if (t < T) wp[t] += adv;
         }
 
-#pragma unroll
-        for (int i = 0; i < QW; i++) cur[i] = nxt[i];
+    };
+
+    for (int c = 0; c < n_chunks; c += 2) {
+        step(bufA, bufB, c);
+        if (c + 1 >= n_chunks) break;
+        step(bufB, bufA, c + 1);
     }
 }
 
