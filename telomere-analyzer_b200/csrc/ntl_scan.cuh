@@ -316,6 +316,11 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
         for (int t = 0; t < 3; t++)
 #pragma unroll
             for (int i = 0; i < 5; i++) cov[t][i] = 0u;
+        /* once the hits of the last pattern exist the planes of this chunk are dead: their registers take chunk c + 2 */
+        auto reload = [&]() {
+            qp += 32 * QW;
+            if ((c + 2) * 32 + lane < n_quads) load_quad(cur, qp + 32 * QW);
+        };
 
         /* ---- main patterns: tracks A and B (get_density_iranges :327-356) */
         NTL_UNROLL_PAT
@@ -329,6 +334,7 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
 #pragma unroll
                 for (int i = 0; i < 4; i++) { hA[i] |= EX[i]; hB[i] |= LE[i]; }
             }
+            if (T < 3 && g == PRM_NMAIN_GROUPS - 1) reload();
             ntl_dilate5(hA, m);
             ntl_dilate5(hB, m);
 #pragma unroll
@@ -347,6 +353,7 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
 #pragma unroll
                     for (int i = 0; i < 4; i++) hC[i] |= EX[i];
                 }
+                if (g == PRM_NTVR_GROUPS - 1) reload();
                 ntl_dilate5(hC, m);
 #pragma unroll
                 for (int i = 0; i < 5; i++) cov[2][i] |= hC[i];
@@ -354,10 +361,6 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
 #pragma unroll
             for (int i = 0; i < 5; i++) cov[2][i] |= cov[1][i];
         }
-
-        /* ---- the planes of this chunk are dead: their registers take chunk c + 2 */
-        qp += 32 * QW;
-        if ((c + 2) * 32 + lane < n_quads) load_quad(cur, qp + 32 * QW);
 
         /* ---- coverage spill from the previous lane, trim to [1, L], popcounts */
         u32 pc[3][4], tot[3];
