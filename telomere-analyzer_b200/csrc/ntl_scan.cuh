@@ -477,14 +477,19 @@ __device__ __forceinline__ void ntl_scan_body(const ntl_scan_args &a)
     const int kq_init = (NTL_LANE_BITS * lane + S - 1) / S;
     const int off_init = kq_init * S - NTL_LANE_BITS * lane;
     const int adv_a = NTL_CHUNK_BITS / S, adv_b = NTL_CHUNK_BITS % S;
-    for (;;) {
+    /* the next work item is claimed (atomic + order[] lookup) while the current read is being scanned, so that only
+     * the read's own tables and first quads are waited for between two reads */
+    auto claim = [&]() -> int {
         int item = 0;
         if (lane == 0) item = (int)atomicAdd(a.counter, 1u);
         item = __shfl_sync(NTL_FULL, item, 0);
-        if (item >= a.n_items) break;
-        const int r = a.order[item];
-        if (a.pass != nullptr && a.pass[r] == 0) continue;
-        ntl_scan_read<NPL>(a, r, lane, kq_init, off_init, adv_a, adv_b);
+        return item < a.n_items ? a.order[item] : -1;
+    };
+    int r = claim();
+    while (r >= 0) {
+        const int r_next = claim();
+        if (a.pass == nullptr || a.pass[r] != 0) ntl_scan_read<NPL>(a, r, lane, kq_init, off_init, adv_a, adv_b);
+        r = r_next;
     }
 }
 
