@@ -173,6 +173,24 @@ __device__ __forceinline__ void ntl_dilate5(u32 (&d)[5], int m)
     }
 }
 
+/* Coverage of hit starts whose intervals cannot overlap (see NTL_J_MAIN_UNBORDERED): every hit bit 2^s becomes the
+ * run 2^(s+m) - 2^s, so the whole array is (H << m) - H: four shifts and one 160-bit borrow chain. */
+__device__ __forceinline__ void ntl_cover_sub(u32 (&d)[5], int m)
+{
+    u32 s[5];
+    s[0] = d[0] << m;
+#pragma unroll
+    for (int i = 1; i < 4; i++) s[i] = __funnelshift_l(d[i - 1], d[i], m);
+    s[4] = __funnelshift_l(d[3], 0u, m);
+    asm("sub.cc.u32 %0, %5, %10;\n\t"
+        "subc.cc.u32 %1, %6, %11;\n\t"
+        "subc.cc.u32 %2, %7, %12;\n\t"
+        "subc.cc.u32 %3, %8, %13;\n\t"
+        "subc.u32 %4, %9, 0;"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4])
+        : "r"(s[0]), "r"(s[1]), "r"(s[2]), "r"(s[3]), "r"(s[4]), "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]));
+}
+
 /* aligned "equal" mask of letter j of one pattern for the lane's 4 words: x[i] bit b <=> position (32 i + b + j)
  * carries a base the letter accepts.  pl: planes [NPL][5], v: validity [5]. */
 template <int NPL, bool TVR>
@@ -335,6 +353,9 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
                 for (int i = 0; i < 4; i++) { hA[i] |= EX[i]; hB[i] |= LE[i]; }
             }
             if (T < 3 && g == PRM_NMAIN_GROUPS - 1) reload();
+#ifdef NTL_JIT
+            if (NTL_J_MAIN_UNBORDERED[g]) ntl_cover_sub(hA, m); else
+#endif
             ntl_dilate5(hA, m);
             ntl_dilate5(hB, m);
 #pragma unroll
@@ -354,6 +375,9 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
                     for (int i = 0; i < 4; i++) hC[i] |= EX[i];
                 }
                 if (g == PRM_NTVR_GROUPS - 1) reload();
+#ifdef NTL_JIT
+                if (NTL_J_TVR_UNBORDERED[g]) ntl_cover_sub(hC, m); else
+#endif
                 ntl_dilate5(hC, m);
 #pragma unroll
                 for (int i = 0; i < 5; i++) cov[2][i] |= hC[i];

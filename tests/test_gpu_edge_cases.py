@@ -101,3 +101,30 @@ def test_only_kept_reads_send_their_window_tables_to_the_host():
             for t in range(one.n_tracks):
                 for a, b in zip(tables[(i, t)], one.windows(0, t)):
                     assert np.array_equal(a, b), (i, t)
+
+
+@pytest.mark.parametrize("patterns", ["TTAGGG", "TTAGGG CCCTAA", "TTAGGG GGGTTA", "ACACAC", "YYAGGG", "TTAGGG TTAGG CCCTAA",
+                                      "AAAAAA", "TTAGGG TTAGGC"])
+def test_exact_coverage_by_subtraction_only_where_hits_cannot_overlap(patterns):
+    """The NVRTC kernel covers the exact hits of an 'unbordered' group of equal-length patterns with (H << m) - H and
+    every other group by dilation; both must give the oracle's coverage on reads made of abutting, overlapping and
+    phase-shifted repeats of the patterns themselves (hits at word and lane-block boundaries included)."""
+    from nanotel_b200 import Scanner
+    rng = np.random.default_rng(len(patterns) * 7919)
+    toks = [t.replace("Y", "C").encode() for t in patterns.split()]
+    seqs = []
+    for i in range(24):
+        parts, total = [], 0
+        while total < 300 + 611 * i:
+            u = toks[int(rng.integers(0, len(toks)))]
+            k = int(rng.integers(1, 40))
+            piece = (u * k)[int(rng.integers(0, len(u))):]
+            if rng.random() < 0.3:
+                piece = piece + bytes(rng.choice(ACGT, int(rng.integers(1, 9))))
+            parts.append(piece); total += len(piece)
+        seqs.append(b"".join(parts))
+    P, recs, passed, win_off, wc = oracle_batch(seqs, patterns, None, 0.6, 100, False, False, False)
+    for jit in (True, False):
+        with Scanner(patterns, None, 0.6, 100, jit=jit, debug_stages=True) as sc:
+            res = sc.scan(seqs)
+            compare_batch(sc, res, seqs, recs, passed, win_off, wc, check_stages=True, label="%s jit=%s" % (patterns, jit))
