@@ -42,6 +42,11 @@ struct ReadView {
     int L;
     int fmt;        /* 0: 2-bit quads of 8 words, 1: 4-bit quads of 16 words */
     int n_words;
+    /* locate kernel only: the two coverage blocks (one word per lane, warp_cov) that get_accurate_start / _end
+     * computed for this (read, track), kept in shared memory so that the partial windows of the final density are
+     * not derived from the read a second time.  ccov[slot * 32 + lane], cwb[slot] = first word or NTL_NONE. */
+    u32 *ccov;
+    int *cwb;
 };
 
 __device__ __forceinline__ u32 rv_word(const ReadView &rv, int plane, int w)
@@ -206,6 +211,14 @@ __device__ __forceinline__ int lanes_popc(u32 bits, int wbase, int lane, int lo,
 /* covered positions of track t inside [lo, hi] (1 <= lo <= hi <= L), recomputed from the read, 992 per step */
 __device__ __noinline__ int local_count(const ReadView &rv, int t, int lo, int hi, int lane)
 {
+    if (rv.cwb != nullptr) {
+#pragma unroll 1
+        for (int slot = 0; slot < 2; slot++) {
+            const int wbc = rv.cwb[slot];                       /* lanes 1..31 hold words wbc + 1 .. wbc + 31 */
+            if (wbc != NTL_NONE && lo >= ((wbc + 1) << 5) && hi < ((wbc + 32) << 5))
+                return lanes_popc(rv.ccov[slot * 32 + lane], wbc, lane, lo, hi);
+        }
+    }
     int total = 0;
     for (int wb = (lo >> 5) - 1; ((wb + 1) << 5) <= hi; wb += 31) {
         u32 hs;
@@ -237,6 +250,7 @@ __global__ void __launch_bounds__(256) ntl_filter_kernel(const ntl_read_args a)
     if (r >= a.n_reads) return;
     ReadView rv;
     rv.L = a.len[r]; rv.fmt = a.fmt[r]; rv.base = a.packed + a.woff[r]; rv.n_words = (rv.L >> 5) + 1;
+    rv.ccov = nullptr; rv.cwb = nullptr;
     int keep = 0;
     if (rv.L >= 1000) {                                         /* :2124 */
         int lo, hi;
@@ -480,9 +494,13 @@ __device__ __forceinline__ double density_of(const ReadView &rv, const WinTab &w
 __device__ __noinline__ int get_accurate_end(const ReadView &rv, int t, int telo_end, int lane)
 {
     if (telo_end == -1) return -1;
-    const int wb = ((telo_end - 99) >> 5) - 1;                           /* lanes 1.. cover [e-99, e+51] */
+    /* lanes 1.. cover [e-99, e+51]; the block starts early enough to hold the window of the final end as well */
+    const int wb = ((telo_end - 99 - 160) >> 5) - 1;
     u32 hs;
     const u32 cov = warp_cov(rv, t, wb, lane, &hs);
+    rv.ccov[32 + lane] = cov;
+    if (lane == 0) rv.cwb[1] = wb;
+    __syncwarp();
     u32 en;
     if (t == 0 && c_prm.raw_hits_A) {
         const u32 hp = __shfl_up_sync(NTL_FULL, hs, 1);
@@ -504,9 +522,13 @@ __device__ __noinline__ int get_accurate_start(const ReadView &rv, int t, int te
 {
     if (telo_start == -1) return telo_start;
     const int s = telo_start;
-    const int wb = ((s - 37) >> 5) - 1;                                  /* lanes 1.. cover [s-37, s+100] */
+    /* lanes 1.. cover [s-37, s+100]; the block starts early enough to hold the final start (search_left) as well */
+    const int wb = ((s - 37 - 64) >> 5) - 1;
     u32 hs;
     const u32 cov = warp_cov(rv, t, wb, lane, &hs);
+    rv.ccov[lane] = cov;
+    if (lane == 0) rv.cwb[0] = wb;
+    __syncwarp();
     u32 st;
     if (t == 0 && c_prm.raw_hits_A) st = hs;
     else {
@@ -766,14 +788,16 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
  * ============================================================================================================= */
 #define NTL_BITS_WORDS 512          /* class bits of up to 16384 windows per warp in shared memory */
 
-__device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *state, int lane, u32 *sbits);
+__device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *state, int lane, u32 *sbits, u32 *ccov, int *cwb);
 
 __global__ void __launch_bounds__(128, 8) ntl_locate_kernel(const ntl_read_args a)
 {
     __shared__ u32 s_bits[4][NTL_BITS_WORDS];
+    __shared__ u32 s_ccov[4][64];
+    __shared__ int s_cwb[4][2];
     const int lane = threadIdx.x & 31;
     /* work item = (candidate read, track): the tracks of a read are independent until the keep rule, so they run
-     * on different warps; cand_state[c] = {tracks done, max interval width, error} joins them */
+     * on different warps; cand_state[c] = {tracks done, width (or -1: error) of track 0, 1, 2} joins them */
     const int T = c_prm.n_tracks;
     const int n_items = (int)a.counters[0] * T;
     for (;;) {
@@ -782,7 +806,8 @@ __global__ void __launch_bounds__(128, 8) ntl_locate_kernel(const ntl_read_args 
         i = __shfl_sync(NTL_FULL, i, 0);
         if (i >= n_items) break;
         const int c = i / T;
-        locate_read(a, a.cand[c], i - c * T, a.cand_state + 4 * (size_t)c, lane, s_bits[threadIdx.x >> 5]);
+        locate_read(a, a.cand[c], i - c * T, a.cand_state + 4 * (size_t)c, lane, s_bits[threadIdx.x >> 5],
+                    s_ccov[threadIdx.x >> 5], s_cwb[threadIdx.x >> 5]);
     }
 }
 
@@ -830,13 +855,17 @@ __device__ __noinline__ bool warp_any_telomeric(const WinTab &w, int lane, u32 *
     return __any_sync(NTL_FULL, tel);
 }
 
-__device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *state, int lane, u32 *sbits)
+__device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *state, int lane, u32 *sbits, u32 *ccov, int *cwb)
 {
     ntl_read_result *res = reinterpret_cast<ntl_read_result *>(a.results) + r;
     ntl_stage *stg = a.stages ? reinterpret_cast<ntl_stage *>(a.stages) + (size_t)r * 3 : nullptr;
 
     ReadView rv;
     rv.L = a.len[r]; rv.fmt = a.fmt[r]; rv.base = a.packed + a.woff[r]; rv.n_words = (rv.L >> 5) + 1;
+    rv.ccov = ccov; rv.cwb = cwb;
+    __syncwarp();                                                   /* the previous item is done with the cache */
+    if (lane < 2) cwb[lane] = NTL_NONE;
+    __syncwarp();
     const int S = c_prm.S, T = c_prm.n_tracks;
     const int n_win = ntl_nwin(rv.L, S);
     int status = rv.fmt ? NTL_READ_IUPAC : 0;
@@ -908,11 +937,16 @@ __device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *stat
          *      keep iff max interval width >= 30 over the tracks (:1847, :1857) */
         if (lane == 0) {
             res->track[t_only] = out[t_only];
-            if (err) atomicOr(&state[2], 1);
-            else atomicMax(&state[1], max_width);
+            /* state = {tracks done, width or -1 (error) of track 0, 1, 2}: own slot, fence, one atomic; the warp
+             * that arrives last reads the other slots past L1 */
+            *reinterpret_cast<volatile int *>(&state[1 + t_only]) = err ? -1 : max_width;
             __threadfence();
             if (atomicAdd(&state[0], 1) == T - 1) {
-                const int any_err = atomicOr(&state[2], 0), mw = atomicMax(&state[1], 0);
+                int any_err = 0, mw = 0;
+                for (int t = 0; t < T; t++) {
+                    const int wdt = __ldcg(&state[1 + t]);
+                    if (wdt < 0) any_err = 1; else if (wdt > mw) mw = wdt;
+                }
                 if (any_err) status |= NTL_READ_REF_ERROR;
                 else if (mw >= 30) status |= NTL_READ_KEEP;
                 res->status = status;
