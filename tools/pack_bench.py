@@ -9,8 +9,9 @@ from nanotel_b200 import Scanner  # noqa: E402
 from nanotel_b200.synth import synth_reads  # noqa: E402
 
 buf, off, meta = synth_reads(int(sys.argv[1]) if len(sys.argv) > 1 else 100000, 20261020)
-for nt in (1, 2, 4, 8, 16, 32):
-    sc = Scanner("YYAGGG", rc=True, host_threads=nt)
+RC = os.environ.get("PACK_RC", "1") == "1"
+for nt in (1, 4, 16):
+    sc = Scanner("YYAGGG", rc=RC, host_threads=nt)
     best = 1e9
     for _ in range(4):
         t0 = time.perf_counter()
