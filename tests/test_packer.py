@@ -10,11 +10,16 @@ NIB = {c: v for c, v in zip(b"ACGTMRWSYKVHDBN", [1, 2, 4, 8, 3, 5, 9, 6, 10, 12,
 NIB.update({ord("-"): 0, ord("+"): 0, ord("."): 0})
 
 
-def _pack(seq: bytes, rc: bool):
+def _pack(seq: bytes, rc: bool, misalign: int = 0):
+    """misalign = 0: a 32-byte aligned destination, as the batch buffers are (the AVX2 path then uses non-temporal
+    stores); otherwise a destination `misalign` words off that alignment (plain stores)."""
     from nanotel_b200 import _lib
     L = _lib.load()
     cap = ((len(seq) >> 5) + 8) * 4 * 4
-    w = np.zeros(cap, np.uint32)
+    raw = np.zeros(cap + 16, np.uint32)
+    skip = ((-raw.ctypes.data) % 32) // 4 + misalign
+    w = raw[skip:skip + cap]
+    assert (w.ctypes.data % 32 == 0) == (misalign == 0)
     fb = C.c_int32()
     n = L.ntl_pack_read(seq, len(seq), int(rc), w.ctypes.data, cap, C.byref(fb))
     assert n > 0, n
@@ -52,7 +57,7 @@ def test_packer_matches_layout(rc):
     lens = list(range(1, 70)) + [95, 96, 97, 127, 128, 129, 255, 256, 257, 383, 384, 385, 1000, 4095, 4096, 4097, 10007]
     for L in lens:
         seq = bytes(rng.choice(np.frombuffer(b"ACGTacgt", np.uint8), L))
-        got, fb = _pack(seq, rc)
+        got, fb = _pack(seq, rc, misalign=L % 3)
         exp, efb = _expected(seq, rc)
         assert not fb and not efb
         assert np.array_equal(got, exp), (L, rc)
