@@ -80,14 +80,22 @@ class Scanner:
         lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=n)
         return arr, lens
 
-    def _results_view(self, ptr: C.c_void_p, n: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+    def _results_view(self, ptr: C.c_void_p, n: int, out=None) -> np.ndarray:
         """The records of the last batch, copied out of the context's pinned buffer (which the next batch reuses):
-        into `out` (RESULT_DTYPE, >= n entries, no allocation and no page faults) or into a fresh array."""
+        into `out` (RESULT_DTYPE, >= n entries, no allocation and no page faults) or into a fresh array.
+        out="view" returns a read-only view of that pinned buffer instead (what the C ABI hands out: valid until the
+        next batch on this Scanner)."""
         if n == 0:
             return np.zeros(0, _lib.RESULT_DTYPE)
         buf = (C.c_char * (n * 64)).from_address(ptr.value)
         # one flat memcpy (a structured-dtype .copy() is ~10x slower)
         src = np.frombuffer(buf, dtype=np.uint8, count=n * 64)
+        if isinstance(out, str):
+            if out != "view":
+                raise ValueError('out must be an array, None or "view"')
+            v = src.view(_lib.RESULT_DTYPE)
+            v.flags.writeable = False
+            return v
         if out is None:
             return src.copy().view(_lib.RESULT_DTYPE)
         if out.dtype != _lib.RESULT_DTYPE or out.ndim != 1 or out.shape[0] < n or not out.flags.c_contiguous:
@@ -95,7 +103,7 @@ class Scanner:
         np.copyto(out[:n].view(np.uint8), src)
         return out[:n]
 
-    def scan(self, seqs: Sequence[bytes], out: Optional[np.ndarray] = None) -> np.ndarray:
+    def scan(self, seqs: Sequence[bytes], out=None) -> np.ndarray:
         """ntl_scan_batch: host ASCII reads in, one RESULT_DTYPE record per read out (a copy)."""
         arr, lens = self._marshal(seqs)
         self._keep = (arr, lens, seqs)
@@ -112,7 +120,7 @@ class Scanner:
         lens = np.diff(offsets).astype(np.int64)
         return buf, ptrs, lens
 
-    def scan_concat(self, buf: np.ndarray, offsets: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+    def scan_concat(self, buf: np.ndarray, offsets: np.ndarray, out=None) -> np.ndarray:
         """ntl_scan_batch_concat: reads given as one ASCII buffer + offsets (read i = buf[offsets[i]:offsets[i+1]])."""
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -147,7 +155,7 @@ class Scanner:
     def wait(self) -> None:
         self._check(self._L.ntl_batch_wait(self._h))
 
-    def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+    def download(self, out=None) -> np.ndarray:
         res = C.c_void_p()
         self._check(self._L.ntl_batch_download(self._h, C.byref(res)))
         return self._results_view(res, self._n, out)
