@@ -87,6 +87,10 @@ def test_only_kept_reads_send_their_window_tables_to_the_host():
         res = sc.scan(seqs, out=out)
         assert np.shares_memory(res, out) and len(res) == len(seqs)
         assert res.tobytes() == sc.scan(seqs).tobytes()
+        view = sc.scan(seqs, out="view")                       # the C ABI's own buffer: no copy, read-only
+        assert view.tobytes() == res.tobytes() and not view.flags.writeable and not view.flags.owndata
+        with pytest.raises(ValueError):
+            sc.scan(seqs, out="copy")
         tm = sc.timings()
         kept = np.flatnonzero(res["status"] & 1)
         assert 0 < len(kept) < len(seqs)
