@@ -310,9 +310,8 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
         for (int k = 0; k < NPL; k++) {
 #pragma unroll
             for (int i = 0; i < 4; i++) pl[k][i] = cur[k * 4 + i];
-            u32 nb = __shfl_sync(NTL_FULL, cur[k * 4], (lane + 1) & 31);
-            u32 nc = __shfl_sync(NTL_FULL, nxt[k * 4], 0);
-            pl[k][4] = lane == 31 ? nc : nb;
+            /* one rotation by a lane: lane 0 offers the first word of the NEXT chunk, which is what lane 31 needs */
+            pl[k][4] = __shfl_sync(NTL_FULL, lane == 0 ? nxt[k * 4] : cur[k * 4], (lane + 1) & 31);
         }
         const int pos0 = (c * 32 + lane) * NTL_LANE_BITS;      /* bit index = 1-based position */
         u32 v[5];
