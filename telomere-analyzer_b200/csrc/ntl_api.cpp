@@ -750,17 +750,21 @@ extern "C" int ntl_batch_download(ntl_ctx *c, const ntl_read_result **results)
     const ntl_read_result *res = (const ntl_read_result *)c->h_results.p;
     c->kept_off.assign((size_t)n, -1);
     int64_t n_kept = 0, elems = 0;
-    for (int32_t i = 0; i < n; i++) n_kept += (res[i].status & NTL_READ_KEEP) ? 1 : 0;
-    if (n_kept > 0) {
-        CK(c, c->h_list.ensure((size_t)n_kept * 16));
+    /* one pass over the records; a kept read went through the locate kernel, so the candidate count bounds the list */
+    const int64_t list_cap = std::min<int64_t>(n, std::max<int64_t>(c->tm.candidates, 0));
+    CK(c, c->h_list.ensure((size_t)list_cap * 16 + 16));
+    {
         int64_t *list = (int64_t *)c->h_list.p;
-        int64_t k = 0;
         for (int32_t i = 0; i < n; i++) {
             if (!(res[i].status & NTL_READ_KEEP)) continue;
-            list[2 * k] = i; list[2 * k + 1] = elems; k++;
+            if (n_kept >= list_cap) return fail(c, NTL_ERR_STATE, "more kept reads than locate candidates");
+            list[2 * n_kept] = i; list[2 * n_kept + 1] = elems; n_kept++;
             c->kept_off[(size_t)i] = elems;
             elems += (((int64_t)res[i].n_win + 7) & ~(int64_t)7) * T;
         }
+    }
+    if (n_kept > 0) {
+        int64_t *list = (int64_t *)c->h_list.p;
         CK(c, c->d_list.ensure((size_t)n_kept * 16));
         CK(c, c->d_kept.ensure((size_t)elems * 2 + 64));
         CK(c, c->h_cum.ensure((size_t)elems * 2 + 64));
