@@ -10,7 +10,7 @@ from nanotel_b200.synth import synth_reads  # noqa: E402
 
 buf, off, meta = synth_reads(int(sys.argv[1]) if len(sys.argv) > 1 else 100000, 20261020)
 RC = os.environ.get("PACK_RC", "1") == "1"
-for nt in (1, 4, 16):
+for nt in [int(x) for x in os.environ.get("PACK_THREADS", "1,4,16").split(",")]:
     sc = Scanner("YYAGGG", rc=RC, host_threads=nt)
     best = 1e9
     for _ in range(4):
