@@ -18,6 +18,7 @@ import io
 import os
 import sys
 import time
+from concurrent.futures import ThreadPoolExecutor
 from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -278,27 +279,33 @@ def write_read_outputs(output_dir: str, reads: Sequence[Read], sc: Scanner, res:
     os.makedirs(rd, exist_ok=True)
     os.makedirs(dv, exist_ok=True)
     min_density = sc.params.min_density
-    for i in order:
-        name, seq = reads[i]
+    suffixes = ("", "_mismatch", "_mismatch_tvr")[:sc.n_tracks]
+    header = ",".join(["ID", "start_index", "end_index"] + [c + sfx for sfx in suffixes for c in ("density", "class")])
+
+    def emit(s: int, name: str, seq: bytes, tables) -> None:
+        """One read's two files.  zlib releases the GIL while it compresses, so these jobs run side by side."""
         if rc_applied:
             seq = revcomp(seq)
-        s = int(serial[i])
         up = seq.upper()
         body = b"\n".join(up[k:k + 80] for k in range(0, len(up), 80))
-        with gzip.open(os.path.join(rd, "%d.fasta.gz" % s), "wb", compresslevel=6) as f:      # R's gzfile() default
-            f.write(b">" + name.encode() + b"\n" + body + b"\n")
-        cols, header = [], ["ID", "start_index", "end_index"]
-        for t, suffix in zip(range(sc.n_tracks), ("", "_mismatch", "_mismatch_tvr")):
-            st, en, cov, den = sc.windows(int(i), t, int(res[i]["n_win"]))
-            cls = np.where(den < min_density, np.where(den < 0.1, 0, 1), -5)        # NanoTel.R:749-758
-            if t == 0:
-                cols += [np.arange(1, len(st) + 1), st, en]
-            cols += [den, cls]
-            header += ["density" + suffix, "class" + suffix]
+        with open(os.path.join(rd, "%d.fasta.gz" % s), "wb") as f:
+            f.write(gzip.compress(b">" + name.encode() + b"\n" + body + b"\n", 6))          # R's gzfile() default
+        st, en = tables[0][0], tables[0][1]
+        cols = [map(str, range(1, len(st) + 1)), map(str, st.tolist()), map(str, en.tolist())]
+        for _, _, _, den in tables:
+            cls = np.where(den < min_density, np.where(den < 0.1, 0, 1), -5)                  # NanoTel.R:749-758
+            cols += [map(repr, den.tolist()), map(str, cls.tolist())]                         # repr: shortest round trip
         with open(os.path.join(dv, "read%d.csv" % s), "w") as f:
-            f.write(",".join(header) + "\n")
-            for row in zip(*cols):
-                f.write(",".join(_fmt_double(v) if isinstance(v, (float, np.floating)) else str(int(v)) for v in row) + "\n")
+            f.write(header + "\n" + "\n".join(map(",".join, zip(*cols))) + "\n")
+
+    # the window tables come from the (single-threaded) context and are collected first -- once the pool runs, the
+    # main thread would wait for the GIL at every call; everything after that is per-read file work
+    order = [int(i) for i in order]
+    tables = [[sc.windows(i, t, int(res[i]["n_win"])) for t in range(sc.n_tracks)] for i in order]
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+        jobs = [pool.submit(emit, int(serial[i]), reads[i][0], reads[i][1], tb) for i, tb in zip(order, tables)]
+        for j in jobs:
+            j.result()
 
 
 # ------------------------------------------------------------------------------------------------ chunk loop
