@@ -6,14 +6,20 @@
  * gzip is transparent (zlib's gzread also passes plain files through), FASTA may be multi-line, FASTQ is 4-line
  * records, names are the full header line without '>' / '@', qualities are skipped.  A chunk comes back as ONE
  * contiguous sequence buffer + offsets -- exactly what ntl_scan_batch_concat() takes -- so no per-read allocation
- * happens between the file and the packer.  The next chunk is inflated and parsed by a background thread while the
- * caller works on the current one.
+ * happens between the file and the packer.  The next chunk is parsed by a background thread while the caller works on
+ * the current one, and the files of the list are inflated side by side: up to NTL_READER_FILES (default 8) files ahead
+ * of the parser each have their own zlib thread feeding a bounded queue of 4 MiB blocks (a nanopore run is thousands
+ * of small fastq.gz files; one gzip stream cannot be inflated in parallel, a list of them can).
  */
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <zlib.h>
+#include <algorithm>
 #include <condition_variable>
+#include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -22,6 +28,71 @@
 #include "../../include/nanotel_b200.h"
 
 namespace {
+
+/* One file being inflated by its own thread into a bounded queue of blocks. */
+struct FileStream {
+    static constexpr size_t BLOCK = 4u << 20;
+    static constexpr size_t DEPTH = 8;
+    struct Block { std::vector<char> data; size_t n = 0; };
+    std::string path;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Block> q;
+    bool finished = false;          /* producer pushed everything it will ever push */
+    bool cancel = false;
+    std::string error;              /* set before finished */
+
+    explicit FileStream(const std::string &p) : path(p) { th = std::thread([this]() { produce(); }); }
+    ~FileStream()
+    {
+        { std::lock_guard<std::mutex> g(mu); cancel = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+    }
+    void finish(const std::string &err)
+    {
+        { std::lock_guard<std::mutex> g(mu); error = err; finished = true; }
+        cv.notify_all();
+    }
+    void produce()
+    {
+        gzFile gz = gzopen(path.c_str(), "rb");
+        if (!gz) { finish("cannot open " + path); return; }
+        gzbuffer(gz, 1u << 20);
+        for (;;) {
+            Block b;
+            b.data.resize(BLOCK);
+            const int got = gzread(gz, b.data.data(), (unsigned)BLOCK);
+            if (got < 0) { int e; std::string m = path + ": " + gzerror(gz, &e); gzclose(gz); finish(m); return; }
+            if (got == 0) break;
+            b.n = (size_t)got;
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [this]() { return cancel || q.size() < DEPTH; });
+            if (cancel) { lk.unlock(); gzclose(gz); return; }
+            q.push_back(std::move(b));
+            lk.unlock();
+            cv.notify_all();
+        }
+        gzclose(gz);
+        finish("");
+    }
+    /* next block, or false at the end of the file / on error (then *err is non-empty) */
+    bool pop(Block *out, std::string *err)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [this]() { return !q.empty() || finished; });
+        if (!q.empty()) {
+            *out = std::move(q.front());
+            q.pop_front();
+            lk.unlock();
+            cv.notify_all();
+            return true;
+        }
+        *err = error;
+        return false;
+    }
+};
 
 struct Chunk {
     std::vector<char> seq, names;
@@ -37,8 +108,12 @@ struct ntl_reader {
     std::vector<std::string> paths;
     bool fastq = true;
     size_t file_idx = 0;
-    gzFile gz = nullptr;
-    std::vector<char> buf;          /* inflate window */
+    bool gz = false;                /* a file is open (its stream is streams[file_idx]) */
+    std::vector<std::unique_ptr<FileStream>> streams;   /* one slot per path; created up to `ahead` files early */
+    size_t started = 0, ahead = 8;
+    FileStream::Block blk;          /* block being copied into buf */
+    size_t blk_pos = 0;
+    std::vector<char> buf;          /* parse window */
     size_t pos = 0, end = 0;
     bool eof_file = true;
     std::string pending_header;     /* FASTA: header of the record that follows the one just finished */
@@ -57,10 +132,19 @@ struct ntl_reader {
         if (pos > 0 && pos < end) memmove(buf.data(), buf.data() + pos, end - pos);
         end -= pos; pos = 0;
         if (end == buf.size()) buf.resize(buf.size() * 2);
-        int got = gzread(gz, buf.data() + end, (unsigned)(buf.size() - end));
-        if (got < 0) { int e; snprintf(err, sizeof err, "%s: %s", paths[file_idx].c_str(), gzerror(gz, &e)); return false; }
-        if (got == 0) { eof_file = true; return false; }
-        end += (size_t)got;
+        if (blk_pos == blk.n) {                       /* next block of the current file */
+            std::string e;
+            blk.n = 0; blk_pos = 0;
+            if (!streams[file_idx]->pop(&blk, &e)) {
+                if (!e.empty()) { snprintf(err, sizeof err, "%s", e.c_str()); return false; }
+                eof_file = true;
+                return false;
+            }
+        }
+        const size_t take = std::min(buf.size() - end, blk.n - blk_pos);
+        memcpy(buf.data() + end, blk.data.data() + blk_pos, take);
+        blk_pos += take;
+        end += take;
         return true;
     }
     /* next line [*b, *e) without the terminator; false at end of file */
@@ -85,14 +169,21 @@ struct ntl_reader {
             }
         }
     }
+    void close_file()
+    {
+        if (gz && file_idx < streams.size()) streams[file_idx].reset();     /* joins the file's thread */
+        gz = false;
+    }
     bool open_next_file()
     {
-        if (gz) { gzclose(gz); gz = nullptr; }
+        gz = false;
         have_pending = false;
         if (file_idx >= paths.size()) return false;
-        gz = gzopen(paths[file_idx].c_str(), "rb");
-        if (!gz) { snprintf(err, sizeof err, "cannot open %s", paths[file_idx].c_str()); return false; }
-        gzbuffer(gz, 1u << 20);
+        if (streams.size() < paths.size()) streams.resize(paths.size());
+        for (; started < paths.size() && started < file_idx + ahead; started++)
+            streams[started].reset(new FileStream(paths[started]));
+        gz = true;
+        blk.n = 0; blk_pos = 0;
         pos = end = 0; eof_file = false;
         return true;
     }
@@ -107,7 +198,7 @@ struct ntl_reader {
             }
             const char *b, *e;
             if (fastq) {
-                if (!line(&b, &e)) { if (err[0]) return NTL_ERR_SEQUENCE; gzclose(gz); gz = nullptr; file_idx++; continue; }
+                if (!line(&b, &e)) { if (err[0]) return NTL_ERR_SEQUENCE; close_file(); file_idx++; continue; }
                 if (b == e) continue;                                   /* blank line between records */
                 if (*b != '@') { snprintf(err, sizeof err, "%s: malformed FASTQ header", paths[file_idx].c_str()); return NTL_ERR_SEQUENCE; }
                 c.names.insert(c.names.end(), b + 1, e);
@@ -122,7 +213,7 @@ struct ntl_reader {
                 if (!have_pending) {
                     bool found = false;
                     while (line(&b, &e)) { if (b < e && *b == '>') { pending_header.assign(b + 1, e); found = true; break; } }
-                    if (!found) { if (err[0]) return NTL_ERR_SEQUENCE; gzclose(gz); gz = nullptr; file_idx++; continue; }
+                    if (!found) { if (err[0]) return NTL_ERR_SEQUENCE; close_file(); file_idx++; continue; }
                 }
                 c.names.insert(c.names.end(), pending_header.begin(), pending_header.end());
                 have_pending = false;
@@ -163,6 +254,7 @@ extern "C" int ntl_reader_open(ntl_reader **out, const char *const *paths, int32
         r->paths.push_back(paths[i]);
     }
     r->buf.resize(4u << 20);
+    if (const char *a = getenv("NTL_READER_FILES")) { const int v = atoi(a); if (v >= 1 && v <= 64) r->ahead = (size_t)v; }
     *out = r;
     return NTL_OK;
 }
@@ -198,6 +290,6 @@ extern "C" void ntl_reader_close(ntl_reader *r)
 {
     if (!r) return;
     if (r->prefetching) r->worker.join();
-    if (r->gz) gzclose(r->gz);
+    r->streams.clear();                                   /* cancels and joins the inflate threads */
     delete r;
 }
