@@ -61,3 +61,33 @@ def test_reader_errors(tmp_path):
         NativeReader([str(bad)], "bam", 10)
     with pytest.raises(ValueError):
         list(NativeReader([str(tmp_path / "missing.fastq")], "fastq", 10))
+
+
+@pytest.mark.parametrize("ahead", ["1", "3", "8"])
+def test_many_files_inflated_side_by_side(tmp_path, monkeypatch, ahead):
+    """A list of many small files (what a nanopore run produces): the files are inflated by their own threads, up to
+    NTL_READER_FILES ahead of the parser; records, their order and the nrec chunking must not depend on that, also when
+    the reader is closed early or a file in the middle is missing."""
+    from nanotel_b200.nanotel import NativeReader, iter_chunks
+    monkeypatch.setenv("NTL_READER_FILES", ahead)
+    rng = np.random.default_rng(11)
+    paths, recs = [], []
+    for j in range(23):
+        p = tmp_path / ("p%02d.fastq%s" % (j, ".gz" if j % 3 else ""))
+        with (gzip.open(p, "wb") if j % 3 else open(p, "wb")) as f:
+            for i in range(int(rng.integers(0, 9))):                     # some files are empty
+                L = int(rng.integers(1, 20000 if j == 5 else 300))      # one file is much larger than a queue block
+                n, s = "f%02d_r%d" % (j, i), bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), L))
+                recs.append((n, s))
+                f.write(b"@" + n.encode() + b"\n" + s + b"\n+\n" + b"#" * L + b"\n")
+        paths.append(str(p))
+    for nrec in (1, 5, 64, 0):
+        got = _native(paths, "fastq", nrec)
+        assert got == list(iter_chunks(paths, "fastq", nrec))
+        assert [r for c in got for r in c] == recs
+    it = iter(NativeReader(paths, "fastq", 3))                           # abandon the reader after the first chunk
+    assert len(next(it)[0]) == 3
+    it.close()
+    missing = paths[:7] + [str(tmp_path / "nope.fastq.gz")] + paths[7:]
+    with pytest.raises(ValueError, match="cannot open"):
+        list(NativeReader(missing, "fastq", 1000))
