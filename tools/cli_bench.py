@@ -1,4 +1,4 @@
-"""Wall clock of the R-free command line on a synthetic gzip FASTQ (cfg2-like reads):  cli_bench.py [n_reads]"""
+"""Wall clock of the R-free command line on synthetic gzip FASTQ files (cfg2-like reads):  cli_bench.py [n_reads] [n_files]"""
 import gzip
 import os
 import subprocess
@@ -14,10 +14,13 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 buf, off, meta = synth_reads(n, 20261022)
 seqs = as_list(buf, off)
 d = tempfile.mkdtemp(prefix="ntl_cli_")
-fq = os.path.join(d, "reads.fastq.gz")
-with gzip.open(fq, "wb", compresslevel=1) as f:
-    for i, s in enumerate(seqs):
-        f.write(b"@read%08d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")
+k = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+fq = os.path.join(d, "in")                              # -i takes a file or a directory of files
+os.makedirs(fq)
+for j in range(k):
+    with gzip.open(os.path.join(fq, "part%03d.fastq.gz" % j), "wb", compresslevel=1) as f:
+        for i in range(j * n // k, (j + 1) * n // k):
+            f.write(b"@read%08d\n" % i + seqs[i] + b"\n+\n" + b"I" * len(seqs[i]) + b"\n")
 env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "telomere-analyzer_b200"))
 for rep in range(2):                                   # the second run finds the NVRTC cubin in the cache
     out = os.path.join(d, "out%d" % rep)
