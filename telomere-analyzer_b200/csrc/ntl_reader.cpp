@@ -7,9 +7,10 @@
  * records, names are the full header line without '>' / '@', qualities are skipped.  A chunk comes back as ONE
  * contiguous sequence buffer + offsets -- exactly what ntl_scan_batch_concat() takes -- so no per-read allocation
  * happens between the file and the packer.  The next chunk is parsed by a background thread while the caller works on
- * the current one, and the files of the list are inflated side by side: up to NTL_READER_FILES (default 8) files ahead
- * of the parser each have their own zlib thread feeding a bounded queue of 4 MiB blocks (a nanopore run is thousands
- * of small fastq.gz files; one gzip stream cannot be inflated in parallel, a list of them can).
+ * the current one, and the files of the list are inflated side by side: up to NTL_READER_FILES (default: the core count, at most 16) files ahead
+ * of the parser each have their own thread that inflates AND parses the file into a bounded queue of record batches
+ * (a nanopore run is thousands of small fastq.gz files; one gzip stream cannot be inflated in parallel, a list of
+ * them can); the consumer only concatenates batches into --nrec chunks.
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -29,21 +30,37 @@
 
 namespace {
 
-/* One file being inflated by its own thread into a bounded queue of blocks. */
+/* Records of one file, parsed: sequence letters and header lines back to back, with their cumulative ends. */
+struct Batch {
+    std::vector<char> seq, names;
+    std::vector<int64_t> seq_end, name_end;
+    int32_t n = 0;
+    void add(const std::string &name) { names.insert(names.end(), name.begin(), name.end()); }
+    void close_record() { seq_end.push_back((int64_t)seq.size()); name_end.push_back((int64_t)names.size()); n++; }
+};
+
+/* One file of the list: its own thread inflates AND parses it into a bounded queue of record batches. */
 struct FileStream {
-    static constexpr size_t BLOCK = 4u << 20;
-    static constexpr size_t DEPTH = 8;
-    struct Block { std::vector<char> data; size_t n = 0; };
+    static constexpr size_t BATCH_BYTES = 2u << 20;
+    static constexpr int32_t BATCH_RECORDS = 1024;
+    size_t depth;                   /* batches a file may run ahead of the consumer (memory budget / files ahead) */
     std::string path;
+    bool fastq;
     std::thread th;
     std::mutex mu;
     std::condition_variable cv;
-    std::deque<Block> q;
-    bool finished = false;          /* producer pushed everything it will ever push */
+    std::deque<Batch> q;
+    bool finished = false;          /* the producer pushed everything it will ever push */
     bool cancel = false;
     std::string error;              /* set before finished */
 
-    explicit FileStream(const std::string &p) : path(p) { th = std::thread([this]() { produce(); }); }
+    /* producer-private: buffered line reader over the gzip stream */
+    gzFile gz = nullptr;
+    std::vector<char> buf;
+    size_t pos = 0, end = 0;
+    std::string zerr;
+
+    FileStream(const std::string &p, bool fq, size_t d) : depth(d), path(p), fastq(fq) { th = std::thread([this]() { produce(); }); }
     ~FileStream()
     {
         { std::lock_guard<std::mutex> g(mu); cancel = true; }
@@ -52,33 +69,22 @@ struct FileStream {
     }
     void finish(const std::string &err)
     {
+        if (gz) { gzclose(gz); gz = nullptr; }
         { std::lock_guard<std::mutex> g(mu); error = err; finished = true; }
         cv.notify_all();
     }
-    void produce()
+    bool push(Batch &&b)            /* false: the reader was closed */
     {
-        gzFile gz = gzopen(path.c_str(), "rb");
-        if (!gz) { finish("cannot open " + path); return; }
-        gzbuffer(gz, 1u << 20);
-        for (;;) {
-            Block b;
-            b.data.resize(BLOCK);
-            const int got = gzread(gz, b.data.data(), (unsigned)BLOCK);
-            if (got < 0) { int e; std::string m = path + ": " + gzerror(gz, &e); gzclose(gz); finish(m); return; }
-            if (got == 0) break;
-            b.n = (size_t)got;
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [this]() { return cancel || q.size() < DEPTH; });
-            if (cancel) { lk.unlock(); gzclose(gz); return; }
-            q.push_back(std::move(b));
-            lk.unlock();
-            cv.notify_all();
-        }
-        gzclose(gz);
-        finish("");
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [this]() { return cancel || q.size() < depth; });
+        if (cancel) return false;
+        q.push_back(std::move(b));
+        lk.unlock();
+        cv.notify_all();
+        return true;
     }
-    /* next block, or false at the end of the file / on error (then *err is non-empty) */
-    bool pop(Block *out, std::string *err)
+    /* next batch, or false at the end of the file / on error (then *err is non-empty) */
+    bool pop(Batch *out, std::string *err)
     {
         std::unique_lock<std::mutex> lk(mu);
         cv.wait(lk, [this]() { return !q.empty() || finished; });
@@ -91,6 +97,96 @@ struct FileStream {
         }
         *err = error;
         return false;
+    }
+
+    bool fill()
+    {
+        if (pos > 0 && pos < end) memmove(buf.data(), buf.data() + pos, end - pos);
+        end -= pos; pos = 0;
+        if (end == buf.size()) buf.resize(buf.size() * 2);
+        const int got = gzread(gz, buf.data() + end, (unsigned)std::min<size_t>(buf.size() - end, 1u << 30));
+        if (got < 0) { int e; zerr = path + ": " + gzerror(gz, &e); return false; }
+        if (got == 0) return false;
+        end += (size_t)got;
+        return true;
+    }
+    /* next line [*b, *e) without the terminator; false at end of file or on a zlib error (zerr set) */
+    bool line(const char **b, const char **e)
+    {
+        for (;;) {
+            const char *nl = (const char *)memchr(buf.data() + pos, '\n', end - pos);
+            if (nl) {
+                *b = buf.data() + pos; *e = nl;
+                pos = (size_t)(nl - buf.data()) + 1;
+                if (*e > *b && (*e)[-1] == '\r') (*e)--;
+                return true;
+            }
+            if (!fill()) {
+                if (!zerr.empty()) return false;
+                if (pos < end) {                 /* last line without '\n' */
+                    *b = buf.data() + pos; *e = buf.data() + end; pos = end;
+                    if (*e > *b && (*e)[-1] == '\r') (*e)--;
+                    return true;
+                }
+                return false;
+            }
+        }
+    }
+    void produce()
+    {
+        gz = gzopen(path.c_str(), "rb");
+        if (!gz) { finish("cannot open " + path); return; }
+        gzbuffer(gz, 1u << 20);
+        buf.resize(4u << 20);
+        Batch bt;
+        std::string pending;            /* FASTA: header of the record that follows the one just finished */
+        bool have_pending = false;
+        const char *b, *e;
+        for (;;) {
+            if (fastq) {
+                if (!line(&b, &e)) break;
+                if (b == e) continue;                                   /* blank line between records */
+                if (*b != '@') { if (bt.n && !push(std::move(bt))) return; finish(path + ": malformed FASTQ header"); return; }
+                bt.names.insert(bt.names.end(), b + 1, e);
+                bool ok = line(&b, &e);
+                if (ok) {
+                    bt.seq.insert(bt.seq.end(), b, e);
+                    const char *pb, *pe;
+                    ok = line(&pb, &pe) && pb != pe && *pb == '+' && line(&pb, &pe);
+                }
+                if (!ok) {
+                    bt.seq.resize(bt.seq_end.empty() ? 0 : (size_t)bt.seq_end.back());          /* drop the partial record */
+                    bt.names.resize(bt.name_end.empty() ? 0 : (size_t)bt.name_end.back());
+                    if (bt.n && !push(std::move(bt))) return;
+                    finish(!zerr.empty() ? zerr : path + ": truncated FASTQ record");
+                    return;
+                }
+            } else {
+                if (!have_pending) {
+                    bool found = false;
+                    while (line(&b, &e)) { if (b < e && *b == '>') { pending.assign(b + 1, e); found = true; break; } }
+                    if (!found) break;
+                }
+                bt.add(pending);
+                have_pending = false;
+                while (line(&b, &e)) {
+                    if (b < e && *b == '>') { pending.assign(b + 1, e); have_pending = true; break; }
+                    bt.seq.insert(bt.seq.end(), b, e);
+                }
+                if (!zerr.empty()) break;
+            }
+            bt.close_record();
+            if (bt.seq.size() >= BATCH_BYTES || bt.n >= BATCH_RECORDS) {
+                if (!push(std::move(bt))) return;
+                bt = Batch();
+            }
+        }
+        if (!zerr.empty()) {
+            bt.seq.resize(bt.seq_end.empty() ? 0 : (size_t)bt.seq_end.back());
+            bt.names.resize(bt.name_end.empty() ? 0 : (size_t)bt.name_end.back());
+        }
+        if (bt.n && !push(std::move(bt))) return;
+        finish(zerr);
     }
 };
 
@@ -108,16 +204,12 @@ struct ntl_reader {
     std::vector<std::string> paths;
     bool fastq = true;
     size_t file_idx = 0;
-    bool gz = false;                /* a file is open (its stream is streams[file_idx]) */
     std::vector<std::unique_ptr<FileStream>> streams;   /* one slot per path; created up to `ahead` files early */
     size_t started = 0, ahead = 8;
-    FileStream::Block blk;          /* block being copied into buf */
-    size_t blk_pos = 0;
-    std::vector<char> buf;          /* parse window */
-    size_t pos = 0, end = 0;
-    bool eof_file = true;
-    std::string pending_header;     /* FASTA: header of the record that follows the one just finished */
-    bool have_pending = false;
+    size_t budget_mb = 2048;        /* parsed records the file threads may hold in total: whole files of a typical run
+                                       fit, so that the files really are inflated side by side */
+    Batch bt;                       /* batch being handed out */
+    int32_t bt_rec = 0;             /* its next record */
     char err[512] = "";
 
     Chunk cur, next;
@@ -125,115 +217,43 @@ struct ntl_reader {
     bool prefetching = false;
     int32_t prefetch_nrec = 0;
 
-    /* ---- buffered line reader over the current file */
-    bool fill()
+    /* Up to `want` records (<= 0: no limit) of the current batch into c; refills the batch from the file list.
+     * Returns the number of records copied, 0 at the end of all files, < 0 on error. */
+    int take(Chunk &c, int32_t want)
     {
-        if (!gz) return false;
-        if (pos > 0 && pos < end) memmove(buf.data(), buf.data() + pos, end - pos);
-        end -= pos; pos = 0;
-        if (end == buf.size()) buf.resize(buf.size() * 2);
-        if (blk_pos == blk.n) {                       /* next block of the current file */
+        while (bt_rec >= bt.n) {
+            if (file_idx >= paths.size()) return 0;
+            if (streams.size() < paths.size()) streams.resize(paths.size());
+            for (; started < paths.size() && started < file_idx + ahead; started++)
+                streams[started].reset(new FileStream(paths[started], fastq,
+                                                      std::max<size_t>(4, (budget_mb << 20) / ahead / FileStream::BATCH_BYTES)));
             std::string e;
-            blk.n = 0; blk_pos = 0;
-            if (!streams[file_idx]->pop(&blk, &e)) {
-                if (!e.empty()) { snprintf(err, sizeof err, "%s", e.c_str()); return false; }
-                eof_file = true;
-                return false;
+            bt = Batch(); bt_rec = 0;
+            if (!streams[file_idx]->pop(&bt, &e)) {
+                if (!e.empty()) { snprintf(err, sizeof err, "%s", e.c_str()); return NTL_ERR_SEQUENCE; }
+                streams[file_idx].reset();                                  /* end of this file: joins its thread */
+                file_idx++;
             }
         }
-        const size_t take = std::min(buf.size() - end, blk.n - blk_pos);
-        memcpy(buf.data() + end, blk.data.data() + blk_pos, take);
-        blk_pos += take;
-        end += take;
-        return true;
-    }
-    /* next line [*b, *e) without the terminator; false at end of file */
-    bool line(const char **b, const char **e)
-    {
-        for (;;) {
-            const char *nl = (const char *)memchr(buf.data() + pos, '\n', end - pos);
-            if (nl) {
-                *b = buf.data() + pos; *e = nl;
-                pos = (size_t)(nl - buf.data()) + 1;
-                if (*e > *b && (*e)[-1] == '\r') (*e)--;
-                return true;
-            }
-            if (!fill()) {
-                if (err[0]) return false;
-                if (pos < end) {                 /* last line without '\n' */
-                    *b = buf.data() + pos; *e = buf.data() + end; pos = end;
-                    if (*e > *b && (*e)[-1] == '\r') (*e)--;
-                    return true;
-                }
-                return false;
-            }
+        const int32_t k = want > 0 ? std::min(want, bt.n - bt_rec) : bt.n - bt_rec;
+        const int64_t s0 = bt_rec ? bt.seq_end[bt_rec - 1] : 0, s1 = bt.seq_end[bt_rec + k - 1];
+        const int64_t m0 = bt_rec ? bt.name_end[bt_rec - 1] : 0, m1 = bt.name_end[bt_rec + k - 1];
+        const int64_t sb = (int64_t)c.seq.size() - s0, mb = (int64_t)c.names.size() - m0;
+        c.seq.insert(c.seq.end(), bt.seq.begin() + s0, bt.seq.begin() + s1);
+        c.names.insert(c.names.end(), bt.names.begin() + m0, bt.names.begin() + m1);
+        for (int32_t i = 0; i < k; i++) {
+            c.seq_off.push_back(bt.seq_end[bt_rec + i] + sb);
+            c.name_off.push_back(bt.name_end[bt_rec + i] + mb);
         }
-    }
-    void close_file()
-    {
-        if (gz && file_idx < streams.size()) streams[file_idx].reset();     /* joins the file's thread */
-        gz = false;
-    }
-    bool open_next_file()
-    {
-        gz = false;
-        have_pending = false;
-        if (file_idx >= paths.size()) return false;
-        if (streams.size() < paths.size()) streams.resize(paths.size());
-        for (; started < paths.size() && started < file_idx + ahead; started++)
-            streams[started].reset(new FileStream(paths[started]));
-        gz = true;
-        blk.n = 0; blk_pos = 0;
-        pos = end = 0; eof_file = false;
-        return true;
-    }
-
-    /* one record into c; returns 1, 0 at end of all files, < 0 on error */
-    int record(Chunk &c)
-    {
-        for (;;) {
-            if (!gz) {
-                if (file_idx >= paths.size()) return 0;
-                if (!open_next_file()) return err[0] ? NTL_ERR_ARG : 0;
-            }
-            const char *b, *e;
-            if (fastq) {
-                if (!line(&b, &e)) { if (err[0]) return NTL_ERR_SEQUENCE; close_file(); file_idx++; continue; }
-                if (b == e) continue;                                   /* blank line between records */
-                if (*b != '@') { snprintf(err, sizeof err, "%s: malformed FASTQ header", paths[file_idx].c_str()); return NTL_ERR_SEQUENCE; }
-                c.names.insert(c.names.end(), b + 1, e);
-                if (!line(&b, &e)) { snprintf(err, sizeof err, "%s: truncated FASTQ record", paths[file_idx].c_str()); return NTL_ERR_SEQUENCE; }
-                c.seq.insert(c.seq.end(), b, e);
-                const char *pb, *pe;
-                if (!line(&pb, &pe) || pb == pe || *pb != '+' || !line(&pb, &pe)) {
-                    snprintf(err, sizeof err, "%s: truncated FASTQ record", paths[file_idx].c_str());
-                    return NTL_ERR_SEQUENCE;
-                }
-            } else {
-                if (!have_pending) {
-                    bool found = false;
-                    while (line(&b, &e)) { if (b < e && *b == '>') { pending_header.assign(b + 1, e); found = true; break; } }
-                    if (!found) { if (err[0]) return NTL_ERR_SEQUENCE; close_file(); file_idx++; continue; }
-                }
-                c.names.insert(c.names.end(), pending_header.begin(), pending_header.end());
-                have_pending = false;
-                while (line(&b, &e)) {
-                    if (b < e && *b == '>') { pending_header.assign(b + 1, e); have_pending = true; break; }
-                    c.seq.insert(c.seq.end(), b, e);
-                }
-                if (err[0]) return NTL_ERR_SEQUENCE;
-            }
-            c.seq_off.push_back((int64_t)c.seq.size());
-            c.name_off.push_back((int64_t)c.names.size());
-            c.n++;
-            return 1;
-        }
+        c.n += k;
+        bt_rec += k;
+        return k;
     }
     void read_chunk(Chunk &c, int32_t nrec)
     {
         c.clear();
         while (nrec <= 0 || c.n < nrec) {
-            int r = record(c);
+            const int r = take(c, nrec > 0 ? nrec - c.n : 0);
             if (r < 0) { c.status = r; return; }
             if (r == 0) break;
         }
@@ -253,8 +273,9 @@ extern "C" int ntl_reader_open(ntl_reader **out, const char *const *paths, int32
         if (!paths[i]) { delete r; return NTL_ERR_ARG; }
         r->paths.push_back(paths[i]);
     }
-    r->buf.resize(4u << 20);
+    r->ahead = std::min<size_t>(16, std::max<size_t>(2, std::thread::hardware_concurrency()));
     if (const char *a = getenv("NTL_READER_FILES")) { const int v = atoi(a); if (v >= 1 && v <= 64) r->ahead = (size_t)v; }
+    if (const char *a = getenv("NTL_READER_MB")) { const int v = atoi(a); if (v >= 16 && v <= (1 << 20)) r->budget_mb = (size_t)v; }
     *out = r;
     return NTL_OK;
 }
