@@ -162,7 +162,8 @@ int ntl_get_stages(const ntl_ctx *ctx, int32_t read_idx, int32_t track, ntl_stag
  * FASTA (multi-line) / FASTQ (4-line records), gzip transparent, records streamed nrec at a time across the file
  * list, names = full header line without '>' / '@', qualities skipped.  A chunk is ONE contiguous sequence buffer
  * + n+1 offsets (what ntl_scan_batch_concat takes) and one name buffer + n+1 offsets; both stay valid until the next
- * ntl_reader_next / ntl_reader_close.  The following chunk is read by a background thread meanwhile. */
+ * ntl_reader_next / ntl_reader_close.  The following chunk is assembled by a background thread meanwhile, and every
+ * file of the list is inflated and parsed by a thread of its own, several files ahead of the one being handed out. */
 typedef struct ntl_reader ntl_reader;
 int  ntl_reader_open(ntl_reader **reader, const char *const *paths, int32_t n_paths, const char *format);
 /* Returns the number of records of the chunk (0 = end of input) or a negative ntl_status. nrec <= 0: everything. */
