@@ -3,8 +3,9 @@ track B = orange polygon of Example/Example_output/single_read_plots_adj/read1.e
 
 Run here (needs /root/reference):  python tests/golden/make_eps_vectors.py
 The polygon is polygon(y = c(0, density, last(density), 0), x = c(1, start_index, L, L)) (NanoTel.R:1331-1338);
-344.00 pt = density 1.0 (read1.eps axis labels 0.0 at 82.89 pt, 1.0 at 426.89 pt).  Only read 1 (30 windows) is
-used: for longer reads the PostScript device merges collinear segments, so vertices no longer map 1:1 to windows.
+344.00 pt = density 1.0 (read1.eps axis labels 0.0 at 82.89 pt, 1.0 at 426.89 pt).  This script covers read 1
+(30 windows, a single run of relative segments); reads 2-4 are extracted by make_eps_polylines.py, which also follows
+the absolute "lineto" anchors the device writes every 100 segments.
 """
 import json
 import os

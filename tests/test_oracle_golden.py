@@ -3,7 +3,8 @@
 * Example/Example_output/summary.csv (2023): start / end / length / density of both tracks for the 4 example reads.
   The example pre-dates the search_left/right_patterns refinement (NanoTel.R:1140-1152), so it pins the stage right
   after get_accurate_start/end (NanoTel.R:1126) -- `acc_*` of the oracle -- and the density arithmetic there.
-* single_read_plots_adj/read1.eps: the per-window density vectors of read 1, tracks A and B.
+* single_read_plots_adj/read1.eps ... read4.eps: the per-window density vectors of all four reads, tracks A and B
+  (987 windows x 2 tracks; for reads 2-4 the integer covered counts follow exactly).
 * the matchPattern example written in NanoTel.R:273-302 (right-hand out-of-bounds hit and trim()).
 Everything after NanoTel.R:1126 has no golden data anywhere: tested below only as restatement regression values
 (an independent throw-away restatement) and marked as such.
@@ -49,6 +50,33 @@ def test_eps_window_densities_of_read1(example_reads):
         dens = res.win_counts[t] / (en - st + 1)
         np.testing.assert_allclose(dens, y[1:31], atol=0.6 / 344.0)   # 0.01 pt resolution, accumulated
         assert abs(y[31] - dens[-1]) < 0.6 / 344.0
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_eps_window_densities_of_reads_2_to_4(example_reads, k):
+    """The polygons of single_read_plots_adj/read<k>.eps hold one vertex per window (204, 594 and 159 windows), rounded
+    to 0.01 pt and re-anchored every 100 segments: the drift stays below 0.5 pt = 0.0015 in density, well under the
+    0.01 between two neighbouring covered counts of a 100-base window, so every window's covered count on both tracks
+    is pinned exactly -- 957 windows x 2 tracks of Biostrings/IRanges output (hits, union, trim, intersect)."""
+    fx = json.load(open(os.path.join(GOLD, "example_reads234_eps_polylines.json")))
+    seq = example_reads[k - 1][1]
+    res = O.analyze_read(O.make_params("TTAGGG"), seq)
+    st, en = O.split_telo(len(seq), 100)
+    n = len(st)
+    for t, key in ((0, "exact"), (1, "mismatch")):
+        poly = fx["reads"][str(k)][key]
+        y = np.asarray(poly["y_pt"]) / fx["pt_per_unit_density"]
+        x = np.asarray(poly["x_pt"])
+        assert len(y) == n + 3 and y[0] == 0.0 and abs(y[-1]) < 2e-3          # c(0, density, last(density), 0)
+        width = en - st + 1
+        counts = res.win_counts[t]
+        np.testing.assert_allclose(counts / width, y[1:n + 1], atol=2e-3)
+        assert np.array_equal(np.rint(y[1:n + 1] * width).astype(int), counts)   # the integer counts themselves
+        assert abs(y[n + 1] - counts[-1] / width[-1]) < 2e-3
+        # x = c(1, start_index, L, L): evenly spaced window starts, then the read end twice
+        scale = x[n + 1] / (len(seq) - 1)
+        np.testing.assert_allclose(x[1:n + 1], (st - 1) * scale, atol=0.6)
+        assert abs(x[n + 2] - x[n + 1]) < 0.02
 
 
 def test_matchpattern_example_from_the_reference_comments():
