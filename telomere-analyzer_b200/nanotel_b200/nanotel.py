@@ -269,6 +269,13 @@ def write_summary_csv(df, path: str) -> None:
             w.writerow(out)
 
 
+def fasta_record(name: str, seq: bytes) -> bytes:
+    """One record as Biostrings::writeXStringSet prints it (NanoTel.R:1870-1873): '>' + the full header line, then the
+    upper-case sequence 80 letters per line."""
+    up = seq.upper()
+    return b">" + name.encode() + b"\n" + b"\n".join(up[k:k + 80] for k in range(0, len(up), 80)) + b"\n"
+
+
 def write_read_outputs(output_dir: str, reads: Sequence[Read], sc: Scanner, res: np.ndarray, serial: np.ndarray,
                        order: Iterable[int], rc_applied: bool = False) -> None:
     """Per telomeric read: reads/<Serial>.fasta.gz (writeXStringSet(compress = TRUE), NanoTel.R:1870-1873) and the
@@ -286,10 +293,8 @@ def write_read_outputs(output_dir: str, reads: Sequence[Read], sc: Scanner, res:
         """One read's two files.  zlib releases the GIL while it compresses, so these jobs run side by side."""
         if rc_applied:
             seq = revcomp(seq)
-        up = seq.upper()
-        body = b"\n".join(up[k:k + 80] for k in range(0, len(up), 80))
         with open(os.path.join(rd, "%d.fasta.gz" % s), "wb") as f:
-            f.write(gzip.compress(b">" + name.encode() + b"\n" + body + b"\n", 6))          # R's gzfile() default
+            f.write(gzip.compress(fasta_record(name, seq), 6))                               # R's gzfile() default
         st, en = tables[0][0], tables[0][1]
         cols = [map(str, range(1, len(st) + 1)), map(str, st.tolist()), map(str, en.tolist())]
         for _, _, _, den in tables:

@@ -129,3 +129,17 @@ def test_shard_bounds_cover_and_balance():
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         per = [int(lens[s:e].sum()) for s, e in b]
         assert max(per) - min(per) <= 2 * 250000
+
+
+def test_fasta_writer_reproduces_the_reference_files():
+    """reads/<Serial>.fasta of the reference's own example run (writeXStringSet): same bytes from fasta_record()."""
+    import hashlib
+    import json
+    from nanotel_b200.nanotel import fasta_record, iter_chunks
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sha = json.load(open(os.path.join(gold, "example_reads_fasta_sha256.json")))
+    (chunk,) = list(iter_chunks([os.path.join(gold, "sample.fasta")], "fasta", 10000))
+    assert len(chunk) == 4
+    for serial, (name, seq) in enumerate(chunk, 1):
+        raw = fasta_record(name, seq)
+        assert len(raw) == sha["bytes"][str(serial)] and hashlib.sha256(raw).hexdigest() == sha["sha256"][str(serial)]

@@ -2,6 +2,8 @@
 oracle's restatement: <basename>_summary.csv, reads_ids.txt, reads/<Serial>.fasta.gz, density vectors."""
 import csv
 import gzip
+import hashlib
+import json
 import os
 
 import numpy as np
@@ -41,6 +43,7 @@ def test_cli_on_the_reference_example(tmp_path):
     from nanotel_b200.nanotel import iter_chunks, main
     inp = os.path.join(GOLD, "sample.fasta")
     out = str(tmp_path / "out")
+    fasta_sha = json.load(open(os.path.join(GOLD, "example_reads_fasta_sha256.json")))
     assert main(["-i", inp, "--save_path", out, "--format", "fasta", "--patterns", "TTAGGG", "--min_density", "0.6"]) == 0
     got = list(csv.reader(open(os.path.join(out, "sample.fasta_summary.csv"))))
     chunks = list(iter_chunks([inp], "fasta", 10000))
@@ -50,8 +53,10 @@ def test_cli_on_the_reference_example(tmp_path):
     ids = open(os.path.join(out, "reads_ids.txt")).read().split("\n")[:-1]
     assert ids == [r[1] for r in exp]
     for serial, (name, seq) in enumerate(chunks[0], 1):                     # all 4 reads are telomeric, Serial = order
-        txt = gzip.open(os.path.join(out, "reads", "%d.fasta.gz" % serial)).read().decode().split("\n")
+        raw = gzip.open(os.path.join(out, "reads", "%d.fasta.gz" % serial)).read()
+        txt = raw.decode().split("\n")
         assert txt[0] == ">" + name and "".join(txt[1:]) == seq.decode() and max(map(len, txt[1:])) == 80
+        assert hashlib.sha256(raw).hexdigest() == fasta_sha["sha256"][str(serial)]      # the reference's own file
         dv = list(csv.DictReader(open(os.path.join(out, "density_vectors", "read%d.csv" % serial))))
         res = O.analyze_read(O.make_params("TTAGGG"), seq)
         st, en = O.split_telo(len(seq), 100)
