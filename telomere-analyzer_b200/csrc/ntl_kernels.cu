@@ -697,34 +697,30 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
                 const int thr_last = (int)a.thr[L - (n_win - 1) * S];
                 bool tel = false;
                 const int full = (n_win - 1) >> 3;               /* groups made of width-S windows only */
-                u32 carry[3] = {0u, 0u, 0u};                     /* last word of the previous step */
+                /* The coverage of the tracks is nested (exact hits c <=1-mismatch hits c those + TVR hits), so a
+                 * window's covered count can only grow from track to track: some track has a telomeric window iff
+                 * the LAST track has one.  Only that plane is walked: half (a third) of the bytes. */
+                const uint16_t *cm = a.cum[T - 1] + wo;
+                const uint4 *cv = reinterpret_cast<const uint4 *>(cm);
+                u32 carry = 0u;                                  /* last word of the previous step */
                 for (int g0 = 0; g0 < full; g0 += 8) {
                     const int g = g0 + sub;
-                    uint4 v[3];
+                    const uint4 v = g < full ? __ldg(cv + g) : make_uint4(0u, 0u, 0u, 0u);
+                    u32 prev = __shfl_up_sync(tmask, v.w, 1, 8);
+                    if (sub == 0) prev = carry;
+                    carry = __shfl_sync(tmask, v.w, 7, 8);
+                    if (g < full) {
+                        /* counts are differences of 16-bit prefixes mod 2^16: kept in the upper half of a word
+                         * ((x << 16) drops the other prefix, the wrap is the 32-bit wrap), so a window costs one
+                         * subtraction and one unsigned compare */
+                        const u32 x[4] = {v.x, v.y, v.z, v.w};
+                        u32 ph = prev & 0xffff0000u;
 #pragma unroll
-                    for (int t = 0; t < 3; t++)
-                        v[t] = (t < T && g < full) ? __ldg(reinterpret_cast<const uint4 *>(a.cum[t] + wo) + g)
-                                                   : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                    for (int t = 0; t < 3; t++) {
-                        if (t < T) {
-                            u32 prev = __shfl_up_sync(tmask, v[t].w, 1, 8);
-                            if (sub == 0) prev = carry[t];
-                            carry[t] = __shfl_sync(tmask, v[t].w, 7, 8);
-                            if (g < full) {
-                                /* counts are differences of 16-bit prefixes mod 2^16: kept in the upper half of a
-                                 * word ((x << 16) drops the other prefix, the wrap is the 32-bit wrap), so a window
-                                 * costs one subtraction and one unsigned compare */
-                                const u32 x[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
-                                u32 ph = prev & 0xffff0000u;
-#pragma unroll
-                                for (int q = 0; q < 4; q++) {
-                                    const u32 xl = x[q] << 16, xh = x[q] & 0xffff0000u;
-                                    tel |= xl - ph >= thr16;
-                                    tel |= xh - xl >= thr16;
-                                    ph = xh;
-                                }
-                            }
+                        for (int q = 0; q < 4; q++) {
+                            const u32 xl = x[q] << 16, xh = x[q] & 0xffff0000u;
+                            tel |= xl - ph >= thr16;
+                            tel |= xh - xl >= thr16;
+                            ph = xh;
                         }
                     }
                 }
@@ -732,14 +728,8 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
                 {
                     const int k = (full << 3) + sub;
                     if (k < n_win) {
-#pragma unroll
-                        for (int t = 0; t < 3; t++) {
-                            if (t < T) {
-                                const uint16_t *cm = a.cum[t] + wo;
-                                const u32 cur = cm[k], pv = k > 0 ? (u32)cm[k - 1] : 0u;
-                                tel |= (int)((cur - pv) & 0xffffu) >= (k == n_win - 1 ? thr_last : thr_reg);
-                            }
-                        }
+                        const u32 cur = cm[k], pv = k > 0 ? (u32)cm[k - 1] : 0u;
+                        tel |= (int)((cur - pv) & 0xffffu) >= (k == n_win - 1 ? thr_last : thr_reg);
                     }
                 }
                 simple = (__ballot_sync(tmask, tel) & tmask) == 0u;
