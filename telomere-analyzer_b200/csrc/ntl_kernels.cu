@@ -703,24 +703,34 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
                 const uint16_t *cm = a.cum[T - 1] + wo;
                 const uint4 *cv = reinterpret_cast<const uint4 *>(cm);
                 u32 carry = 0u;                                  /* last word of the previous step */
-                for (int g0 = 0; g0 < full; g0 += 8) {
-                    const int g = g0 + sub;
-                    const uint4 v = g < full ? __ldg(cv + g) : make_uint4(0u, 0u, 0u, 0u);
-                    u32 prev = __shfl_up_sync(tmask, v.w, 1, 8);
-                    if (sub == 0) prev = carry;
-                    carry = __shfl_sync(tmask, v.w, 7, 8);
-                    if (g < full) {
-                        /* counts are differences of 16-bit prefixes mod 2^16: kept in the upper half of a word
-                         * ((x << 16) drops the other prefix, the wrap is the 32-bit wrap), so a window costs one
-                         * subtraction and one unsigned compare */
-                        const u32 x[4] = {v.x, v.y, v.z, v.w};
-                        u32 ph = prev & 0xffff0000u;
+                constexpr int NJ = 4;                            /* independent 16-byte loads in flight per lane */
+                for (int g0 = 0; g0 < full; g0 += 8 * NJ) {
+                    uint4 vv[NJ];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const u32 xl = x[q] << 16, xh = x[q] & 0xffff0000u;
-                            tel |= xl - ph >= thr16;
-                            tel |= xh - xl >= thr16;
-                            ph = xh;
+                    for (int j = 0; j < NJ; j++) {
+                        const int g = g0 + 8 * j + sub;
+                        vv[j] = g < full ? __ldg(cv + g) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NJ; j++) {
+                        const int g = g0 + 8 * j + sub;
+                        const uint4 v = vv[j];
+                        u32 prev = __shfl_up_sync(tmask, v.w, 1, 8);
+                        if (sub == 0) prev = carry;
+                        carry = __shfl_sync(tmask, v.w, 7, 8);
+                        if (g < full) {
+                            /* counts are differences of 16-bit prefixes mod 2^16: kept in the upper half of a word
+                             * ((x << 16) drops the other prefix, the wrap is the 32-bit wrap), so a window costs one
+                             * subtraction and one unsigned compare */
+                            const u32 x[4] = {v.x, v.y, v.z, v.w};
+                            u32 ph = prev & 0xffff0000u;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const u32 xl = x[q] << 16, xh = x[q] & 0xffff0000u;
+                                tel |= xl - ph >= thr16;
+                                tel |= xh - xl >= thr16;
+                                ph = xh;
+                            }
                         }
                     }
                 }
