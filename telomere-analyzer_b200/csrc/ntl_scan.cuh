@@ -10,7 +10,8 @@
  * Mapping to the machine (B200: 148 SMs, 32-wide warps, LDG.256, 64-lane/clk integer pipe):
  *   - one warp streams one read, longest reads first (dynamic work counter), 4096 positions per step:
  *     lane l owns 128 consecutive positions = one 32-byte quad {lo[4], hi[4]}, fetched with one LDG.256
- *     (1 KiB per warp per step, fully coalesced); the next step's quad is prefetched into registers;
+ *     (1 KiB per warp per step, fully coalesced); two register buffers swap roles every step, so the quad of step
+ *     c + 2 is requested as soon as the hits of step c exist and nothing waits for a load it has just issued;
  *   - matching is Shift-And in its position-parallel form: one 32-bit word holds 32 text positions, a pattern
  *     letter is one boolean function of the two bit-planes (LOP3), its j-th letter is aligned with a funnel
  *     shift, and letters are combined three at a time into an (all equal, at most one differs) pair
@@ -19,8 +20,11 @@
  *     positions outside [1, L] carry an all-zero "equal" mask, which reproduces Biostrings' rule that
  *     out-of-bounds letters are mismatches (hits may start at 0 or end at L+1 with one mismatch, App. B.3);
  *   - coverage (IRanges::union of the hit intervals, then trim) = hit-start mask dilated by the pattern length
- *     with log-step funnel shifts; the <= 17 bits that spill into the next lane travel by one shuffle;
- *   - window counts: per-lane popcounts, one packed warp scan per step, and every window end that falls into a
+ *     with ternary / doubling funnel-shift steps -- or, for a group of patterns whose exact hits cannot overlap
+ *     (NTL_J_MAIN/TVR_UNBORDERED, decided on the host), the single 160-bit subtraction (H << m) - H; the <= 17 bits
+ *     that spill into the next lane travel by one shuffle;
+ *   - window counts: per-lane popcounts, one packed warp scan per step (its adds are IMADs, the integer ALU pipe is
+ *     the kernel's limiter), and every window end that falls into a
  *     lane's 128 positions is written by that lane as the running prefix "covered bases in [1, window end]"
  *     (uint16, mod 2^16).  Each prefix is written exactly once: no atomics, no zero-fill.  Consumers take
  *     differences.
