@@ -2,15 +2,18 @@
  * ntl_kernels.cu -- sm_100a kernels of libnanotel_b200 other than the JIT-specialised scan:
  *   K2  ntl_scan_kernel<2|4>   runtime-pattern build of ntl_scan.cuh (any pattern set; 4-plane build for IUPAC reads)
  *   K4  ntl_filter_kernel      --use_filter edge filter            (filter_reads/filter_density, NanoTel.R:2083-2163)
- *   K3  ntl_locate_kernel      per-read locator and refinement     (find_telo_position_wraper NanoTel.R:1080-1155 and
- *                              everything it calls, analyze_read's densities and keep rule :1840-1868)
+ *   K3a ntl_triage_kernel      eight lanes per read: proves that a read has no telomeric window on any track and no
+ *                              hit in its first 18 bases and writes its (trivial) record, or hands it to K3b
+ *   K3b ntl_locate_kernel      one warp per (candidate read, track): locator and refinement (find_telo_position_wraper
+ *                              NanoTel.R:1080-1155 and everything it calls, analyze_read's densities and keep rule
+ *                              :1840-1868)
+ *       ntl_gather_windows_kernel   window prefixes of the kept reads, packed for the device-to-host copy
  *
- * K3/K4 are one warp per read with warp-uniform control flow.  Where the reference consults its range list
- * (get_accurate_start/end, get_sub_density on arbitrary intervals) K3 re-derives hits and coverage locally from
- * the packed read -- one word (32 positions) per lane, the same bit-parallel matching as K2 -- so that K2 never has
- * to spill per-base masks to HBM.  Reads whose tracks have no telomeric window at all (K2 leaves a flag) skip the
- * window table entirely.  All fp64 expressions are written exactly as NanoTel.R evaluates them (int/int divisions
- * in double, sums in window order); this file must be compiled with --fmad=false.
+ * Control flow inside a team / warp is uniform.  Where the reference consults its range list (get_accurate_start/end,
+ * get_sub_density on arbitrary intervals) K3b re-derives hits and coverage locally from the packed read -- one word
+ * (32 positions) per lane, the same bit-parallel matching as K2 -- so that K2 never has to spill per-base masks to
+ * HBM.  All fp64 expressions are written exactly as NanoTel.R evaluates them (int/int divisions in double, sums in
+ * window order); this file must be compiled with --fmad=false.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -661,9 +664,9 @@ __device__ __forceinline__ bool triage_first_window_hit(u32 lo, u32 hi, int T)
     return any;
 }
 
-/* Eight lanes per read ("team"), four reads per warp: the team walks the read's window prefixes eight 16-byte
- * groups at a time (128 contiguous bytes per track and step), so the longest read costs n_win / 64 dependent steps
- * instead of n_win / 8, and the loads of a team coalesce. */
+/* Eight lanes per read ("team"), four reads per warp: the team walks the window prefixes of the read's LAST track
+ * (see below) 32 16-byte groups at a time (four independent loads per lane, 512 contiguous bytes per team and step),
+ * so the longest read costs n_win / 256 dependent steps, and the loads of a team coalesce. */
 __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
 {
     const int lane = threadIdx.x & 31;
