@@ -234,13 +234,68 @@ int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst)
     return 0;
 }
 
+#if defined(__x86_64__)
+/* Full 32-letter blocks of a read with IUPAC letters -> the four nibble planes, 32 letters per iteration: letter ->
+ * Biostrings nibble through two 16-entry byte shuffles ((c | 0x20) - 0x60 is 1..26 for a letter), --rc = byte
+ * reversal + a third shuffle that mirrors the nibble (A<->T, C<->G), one movemask per plane.  Returns the number of
+ * blocks done and leaves the carried top bits in carry[]; stops early (blocks done so far) at the first block that
+ * holds anything but IUPAC letters -- gap characters and errors are left to the scalar loop. */
+__attribute__((target("avx2")))
+static int64_t pack_blocks_4bit_avx2(const char *s, int64_t L, int rc, uint32_t *dst, uint32_t carry[4])
+{
+    alignas(32) uint8_t t0[32], t1[32], tc[32];
+    for (int i = 0; i < 16; i++) {
+        t0[i] = t0[i + 16] = g_nib[0x60 + i] == 0 ? 0xFF : g_nib[0x60 + i];          /* '`' a .. o */
+        t1[i] = t1[i + 16] = (0x70 + i) <= 'z' ? g_nib[0x70 + i] : 0xFF;             /* p .. z     */
+        tc[i] = tc[i + 16] = comp_nib((uint8_t)i);
+    }
+    t0[0] = t0[16] = 0xFF;
+    const __m256i T0 = _mm256_load_si256((const __m256i *)t0), T1 = _mm256_load_si256((const __m256i *)t1);
+    const __m256i TC = _mm256_load_si256((const __m256i *)tc);
+    const __m256i rev = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0,
+                                         15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    const __m256i c20 = _mm256_set1_epi8(0x20), c60 = _mm256_set1_epi8(0x60), m0f = _mm256_set1_epi8(0x0f);
+    const int64_t nb = L >> 5;
+    for (int64_t k = 0; k < nb; k++) {
+        __m256i v;
+        if (rc) {
+            v = _mm256_loadu_si256((const __m256i *)(s + (L - 32 - (k << 5))));
+            v = _mm256_shuffle_epi8(v, rev);
+            v = _mm256_permute2x128_si256(v, v, 0x01);
+        } else v = _mm256_loadu_si256((const __m256i *)(s + (k << 5)));
+        const __m256i idx = _mm256_sub_epi8(_mm256_or_si256(v, c20), c60);           /* 1..26 for letters */
+        const __m256i in = _mm256_and_si256(_mm256_cmpgt_epi8(idx, _mm256_setzero_si256()),
+                                            _mm256_cmpgt_epi8(_mm256_set1_epi8(27), idx));
+        const __m256i lo4 = _mm256_and_si256(idx, m0f);
+        __m256i nib = _mm256_blendv_epi8(_mm256_shuffle_epi8(T0, lo4), _mm256_shuffle_epi8(T1, lo4), _mm256_slli_epi16(idx, 3));
+        /* not a letter, or a letter outside the IUPAC alphabet (table entry 0xFF): leave the block to the scalar loop */
+        const __m256i bad = _mm256_or_si256(_mm256_cmpeq_epi8(nib, _mm256_set1_epi8(-1)), _mm256_xor_si256(in, _mm256_set1_epi8(-1)));
+        if (_mm256_movemask_epi8(bad) != 0) return k;
+        if (rc) nib = _mm256_shuffle_epi8(TC, nib);
+        for (int b = 0; b < 4; b++) {
+            const uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(nib, 7 - b));
+            dst[(k >> 2) * 16 + b * 4 + (k & 3)] = (m << 1) | carry[b];
+            carry[b] = m >> 31;
+        }
+    }
+    return nb;
+}
+#endif
+
 int ntl_pack_read_4bit(const char *s, int64_t L, int rc, uint32_t *dst)
 {
     init_tables();
     const int64_t n_words = (L >> 5) + 1;
     const int64_t n_quads = (n_words + 3) >> 2;
-    memset(dst, 0, (size_t)n_quads * 16 * sizeof(uint32_t));
-    for (int64_t p = 1; p <= L; p++) {
+    int64_t done = 0;                                   /* 32-letter blocks (= words, up to the carried bit) finished */
+    uint32_t carry[4] = {0u, 0u, 0u, 0u};
+#if defined(__x86_64__)
+    if (g_have_avx2) done = pack_blocks_4bit_avx2(s, L, rc, dst, carry);
+#endif
+    /* the words from `done` on: zero, the carried bits, then the remaining letters one by one */
+    for (int64_t w = done; w < n_quads * 4; w++)
+        for (int b = 0; b < 4; b++) dst[(w >> 2) * 16 + b * 4 + (w & 3)] = w == done ? carry[b] : 0u;
+    for (int64_t p = (done << 5) + 1; p <= L; p++) {
         unsigned char c = rc ? (unsigned char)s[L - p] : (unsigned char)s[p - 1];
         uint8_t nb = g_nib[c];
         if (nb == 0xFF) return -1;

@@ -72,6 +72,35 @@ def test_packer_matches_layout(rc):
         assert fb and efb and np.array_equal(got, exp), (L, rc)
 
 
+@pytest.mark.parametrize("rc", [False, True])
+def test_iupac_reads_take_the_vector_path_and_fall_back_on_gaps(rc):
+    """4-bit reads: 32-letter blocks of IUPAC letters are packed by the AVX2 loop, the first block holding a gap
+    character (or the tail) hands over to the scalar loop with the carried bits; every hand-over point is tried."""
+    rng = np.random.default_rng(99)
+    iupac = np.frombuffer(b"ACGTMRWSYKVHDBNacgtmrwsykvhdbn", np.uint8)
+    for L in list(range(1, 100)) + [127, 128, 129, 1000, 4097]:
+        seq = bytearray(rng.choice(iupac, L))
+        seq[int(rng.integers(0, L))] = ord("N")                         # at least one non-ACGT letter
+        got, fb = _pack(bytes(seq), rc, misalign=L % 2)
+        exp, efb = _expected(bytes(seq), rc)
+        assert fb and efb and np.array_equal(got, exp), (L, rc)
+    for gap_at in (0, 31, 32, 63, 64, 100, 299):
+        seq = bytearray(rng.choice(iupac, 300))
+        seq[gap_at] = ord("-+."[gap_at % 3])
+        got, fb = _pack(bytes(seq), rc)
+        exp, efb = _expected(bytes(seq), rc)
+        assert fb and efb and np.array_equal(got, exp), (gap_at, rc)
+    for bad_at in (5, 40, 170):                                         # a letter outside the alphabet, any block
+        seq = bytearray(rng.choice(iupac, 200))
+        seq[3] = ord("N")
+        seq[bad_at] = ord("J")
+        from nanotel_b200 import _lib
+        L_ = _lib.load()
+        w = np.zeros(4096, np.uint32)
+        fbv = C.c_int32()
+        assert L_.ntl_pack_read(bytes(seq), len(seq), int(rc), w.ctypes.data, 4096, C.byref(fbv)) < 0
+
+
 def test_packer_rejects_non_dna():
     from nanotel_b200 import _lib
     L = _lib.load()
