@@ -70,6 +70,7 @@ def test_many_files_inflated_side_by_side(tmp_path, monkeypatch, ahead):
     the reader is closed early or a file in the middle is missing."""
     from nanotel_b200.nanotel import NativeReader, iter_chunks
     monkeypatch.setenv("NTL_READER_FILES", ahead)
+    monkeypatch.setenv("NTL_READER_MB", "16" if ahead == "3" else "2048")   # tiny budget: the file threads must block
     rng = np.random.default_rng(11)
     paths, recs = [], []
     for j in range(23):
