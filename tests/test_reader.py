@@ -92,3 +92,34 @@ def test_many_files_inflated_side_by_side(tmp_path, monkeypatch, ahead):
     missing = paths[:7] + [str(tmp_path / "nope.fastq.gz")] + paths[7:]
     with pytest.raises(ValueError, match="cannot open"):
         list(NativeReader(missing, "fastq", 1000))
+
+
+def test_file_thread_blocks_on_a_full_queue(tmp_path, monkeypatch):
+    """A file much larger than its share of the memory budget: its thread has to wait for the consumer again and
+    again; nothing may be lost, reordered or deadlock, also when the reader is dropped half way."""
+    from nanotel_b200.nanotel import NativeReader
+    monkeypatch.setenv("NTL_READER_FILES", "8")
+    monkeypatch.setenv("NTL_READER_MB", "16")                           # 4 batches of 2 MiB per file
+    rng = np.random.default_rng(5)
+    big = tmp_path / "big.fastq.gz"
+    base = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 3000))
+    n = 8000                                                            # 24 MB of sequence
+    with gzip.open(big, "wb", compresslevel=1) as f:
+        for i in range(n):
+            s = base[i % 100:] + base[:i % 100]
+            f.write(b"@r%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    small = tmp_path / "small.fastq"
+    small.write_bytes(b"@last\nACGT\n+\nIIII\n")
+    got = 0
+    for names, buf, off in NativeReader([str(big), str(small)], "fastq", 1500):
+        for j, nm in enumerate(names):
+            i = got + j
+            if i < n:
+                assert nm == "r%d" % i and buf[int(off[j]):int(off[j + 1])].tobytes() == base[i % 100:] + base[:i % 100]
+            else:
+                assert nm == "last" and buf[int(off[j]):int(off[j + 1])].tobytes() == b"ACGT"
+        got += len(names)
+    assert got == n + 1
+    it = iter(NativeReader([str(big), str(small)], "fastq", 10))
+    next(it)
+    it.close()                                                          # the blocked file thread must let go
