@@ -417,7 +417,9 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
     int32_t *h_order = (int32_t *)(mb + c->off_order);
     uint8_t *h_fmt = (uint8_t *)(mb + c->off_fmt);
 
-    int64_t words = 0, wins = 0, bases = 0;
+    /* what the packer needs (lengths, word offsets) first; the window offsets, which cost a division per read, are
+     * computed by win_tables() -- in overlap mode while the worker threads are already packing */
+    int64_t words = 0, bases = 0;
     for (int32_t i = 0; i < n; i++) {
         const int64_t L = len[i];
         if (L < 1) return fail(c, NTL_ERR_SEQUENCE, "read %d has length %lld: NanoTel.R stops on empty reads (seq(1, 0, by = S), :216)", i, (long long)L);
@@ -425,16 +427,22 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
         if (!seq[i]) return fail(c, NTL_ERR_ARG, "read %d: NULL sequence", i);
         h_len[i] = (int32_t)L;
         h_woff[i] = words;
-        h_winoff[i] = wins;
         h_fmt[i] = 0;
         const int64_t n_words = (L >> 5) + 1;
         words += ((n_words + 3) >> 2) * 8;
-        wins += ((int64_t)count_windows(L, S) + 7) & ~(int64_t)7;   /* each read starts on a 16-byte boundary of the uint16 planes */
         bases += L;
     }
+    auto win_tables = [&]() {
+        int64_t wins = 0;
+        for (int32_t i = 0; i < n; i++) {
+            h_winoff[i] = wins;
+            wins += ((int64_t)count_windows(h_len[i], S) + 7) & ~(int64_t)7;   /* each read starts on a 16-byte boundary of the uint16 planes */
+        }
+        c->total_windows = wins;
+    };
+    if (!overlap) win_tables();
     tr.mark("tables");
     const int64_t main_words = words;
-    c->total_windows = wins;
     c->bases = bases;
     CK(c, c->h_packed.ensure((size_t)main_words * 4 + 64));
     uint32_t *hp = (uint32_t *)c->h_packed.p;
@@ -478,9 +486,6 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
         ntl_parallel_for(n, c->host_threads, 64, pack_range);
     } else {
         c->meta_bytes = off;
-        int rc0 = ensure_device_buffers(c, main_words);
-        if (rc0 != NTL_OK) return rc0;
-        CK(c, cudaEventRecord(c->ev[0], c->stream));
         const int64_t grain = 64, ngr = (n + grain - 1) / grain;
         const int64_t piece = 2 << 20;          /* 8 MiB */
         std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[(size_t)ngr + 1]);
@@ -499,8 +504,18 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
         };
         std::vector<std::thread> th;
         for (int t = 1; t < c->host_threads && t < ngr; t++) th.emplace_back(worker);
+        win_tables();                           /* the packers do not need these */
         work_order();                           /* h_fmt is all zero here; redone below if a read needs 4 bits */
-        cudaError_t cerr = cudaMemcpyAsync(c->d_meta.p, c->h_meta.p, c->meta_bytes, cudaMemcpyHostToDevice, c->stream);
+        cudaError_t cerr = cudaSuccess;
+        {
+            const int rc0 = ensure_device_buffers(c, main_words);      /* needs total_windows */
+            if (rc0 != NTL_OK || cudaEventRecord(c->ev[0], c->stream) != cudaSuccess) {
+                next.store(ngr);                                        /* stop the packers, then report */
+                for (auto &t : th) t.join();
+                return rc0 != NTL_OK ? rc0 : fail(c, NTL_ERR_CUDA, "cudaEventRecord failed");
+            }
+        }
+        cerr = cudaMemcpyAsync(c->d_meta.p, c->h_meta.p, c->meta_bytes, cudaMemcpyHostToDevice, c->stream);
         int64_t uf = 0;
         for (;;) {
             while (uf < ngr && done[uf].load(std::memory_order_acquire)) uf++;
@@ -551,7 +566,7 @@ static int pack_internal(ntl_ctx *c, const char *const *seq, const int64_t *len,
     c->tm.pack_ms = now_ms() - t0;
     c->tm.bases = bases;
     c->tm.packed_bytes = words * 4;
-    c->tm.window_bytes = wins * 2 * c->dev.n_tracks;
+    c->tm.window_bytes = c->total_windows * 2 * c->dev.n_tracks;
     c->state = ST_PACKED;
     if (overlap) {
         /* the 4-bit arena (if any) and the tables follow; a grown device buffer means starting the copy over */
