@@ -78,7 +78,7 @@ struct ntl_ctx {
     ntl_params prm;
     std::vector<std::string> pat_store, tvr_store;
     ntl_dev_params dev;
-    int device = 0, n_sms = 0, scan_grid = 0, locate_grid = 0, host_threads = 1;
+    int device = 0, n_sms = 0, scan_grid = 0, scan_grid4 = 0, locate_grid = 0, host_threads = 1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr};
     cudaEvent_t ring[NTL_EVENT_RING][5] = {{nullptr}};
@@ -313,8 +313,10 @@ extern "C" int ntl_create(ntl_ctx **out, const ntl_params *p)
             return NTL_ERR_JIT;
         }
         if (c->jit) {
-            int jb = ntl_jit_blocks_per_sm(c->jit);
+            int jb = ntl_jit_blocks_per_sm(c->jit, 0);
             if (jb >= 1) c->scan_grid = c->n_sms * jb;
+            jb = ntl_jit_blocks_per_sm(c->jit, 1);
+            c->scan_grid4 = c->n_sms * (jb >= 1 ? jb : 1);
         } else {
             snprintf(c->err, sizeof c->err, "note: JIT unavailable (%s); using the runtime-pattern scan kernel", jerr.c_str());
         }
@@ -681,7 +683,7 @@ extern "C" int ntl_batch_enqueue(ntl_ctx *c)
         sa.n_items = c->n2;
         sa.counter = (uint32_t *)c->d_counter.p;
         if (c->jit) {
-            cudaError_t e = ntl_jit_launch(c->jit, &sa, c->scan_grid, c->stream);
+            cudaError_t e = ntl_jit_launch(c->jit, &sa, 0, c->scan_grid, c->stream);
             if (e != cudaSuccess) return fail(c, NTL_ERR_CUDA, "JIT scan kernel launch failed: %s", cudaGetErrorString(e));
             c->tm.scan_is_jit = 1;
         } else {
@@ -693,7 +695,12 @@ extern "C" int ntl_batch_enqueue(ntl_ctx *c)
         sa.order = (const int32_t *)(dm + c->off_order) + c->n2;
         sa.n_items = c->n4;
         sa.counter = (uint32_t *)c->d_counter.p + 8;
-        CK(c, ntl_k_scan(&sa, 1, c->scan_grid, c->stream));
+        if (c->jit) {
+            cudaError_t e = ntl_jit_launch(c->jit, &sa, 1, c->scan_grid4, c->stream);
+            if (e != cudaSuccess) return fail(c, NTL_ERR_CUDA, "JIT scan kernel (IUPAC reads) launch failed: %s", cudaGetErrorString(e));
+        } else {
+            CK(c, ntl_k_scan(&sa, 1, c->scan_grid, c->stream));
+        }
         launches++;
     }
     CK(c, cudaEventRecord(ev[2], c->stream));

@@ -13,7 +13,8 @@ ntl_jit_kernel *ntl_jit_build(const ntl_dev_params *prm, int major, int minor, s
 /* Compile only (no device needed): returns the cubin size or < 0; log receives the NVRTC log / error. */
 long ntl_jit_compile(const ntl_dev_params *prm, const char *arch, std::string *cubin, std::string *log);
 std::string ntl_jit_source(const ntl_dev_params *prm);      /* the generated prologue + kernel entry */
-cudaError_t ntl_jit_launch(ntl_jit_kernel *k, const ntl_scan_args *a, int grid, cudaStream_t st);
-int ntl_jit_blocks_per_sm(ntl_jit_kernel *k);
+/* four_bit: the build for reads with IUPAC letters (four nibble planes) instead of the 2-bit one */
+cudaError_t ntl_jit_launch(ntl_jit_kernel *k, const ntl_scan_args *a, int four_bit, int grid, cudaStream_t st);
+int ntl_jit_blocks_per_sm(ntl_jit_kernel *k, int four_bit);
 void ntl_jit_free(ntl_jit_kernel *k);
 #endif

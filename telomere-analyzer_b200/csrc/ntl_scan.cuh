@@ -221,8 +221,13 @@ __device__ __forceinline__ void ntl_letter(int p, int j, const u32 (&pl)[NPL][5]
     }
 #else
 #pragma unroll
-    for (int i = 0; i < 5; i++)
-        e[i] = TVR ? ntl_jit_eq_tvr(p, j, pl[1][i], pl[0][i], v[i]) : ntl_jit_eq_main(p, j, pl[1][i], pl[0][i], v[i]);
+    for (int i = 0; i < 5; i++) {
+        if constexpr (NPL == 2)
+            e[i] = TVR ? ntl_jit_eq_tvr(p, j, pl[1][i], pl[0][i], v[i]) : ntl_jit_eq_main(p, j, pl[1][i], pl[0][i], v[i]);
+        else
+            e[i] = TVR ? ntl_jit_eq4_tvr(p, j, pl[0][i], pl[1][i], pl[2][i], pl[3][i], v[i])
+                       : ntl_jit_eq4_main(p, j, pl[0][i], pl[1][i], pl[2][i], pl[3][i], v[i]);
+    }
 #endif
 #pragma unroll
     for (int i = 0; i < 4; i++) x[i] = ntl_fsr(e[i], e[i + 1], j);
@@ -357,7 +362,7 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
             }
             if (T < 3 && g == PRM_NMAIN_GROUPS - 1) reload();
 #ifdef NTL_JIT
-            if (NTL_J_MAIN_UNBORDERED[g]) ntl_cover_sub(hA, m); else
+            if (NPL == 2 && NTL_J_MAIN_UNBORDERED[g]) ntl_cover_sub(hA, m); else      /* IUPAC read letters can make hits overlap */
 #endif
             ntl_dilate5(hA, m);
             ntl_dilate5(hB, m);
@@ -379,7 +384,7 @@ __device__ __forceinline__ void ntl_scan_read(const ntl_scan_args &a, int r, int
                 }
                 if (g == PRM_NTVR_GROUPS - 1) reload();
 #ifdef NTL_JIT
-                if (NTL_J_TVR_UNBORDERED[g]) ntl_cover_sub(hC, m); else
+                if (NPL == 2 && NTL_J_TVR_UNBORDERED[g]) ntl_cover_sub(hC, m); else
 #endif
                 ntl_dilate5(hC, m);
 #pragma unroll
