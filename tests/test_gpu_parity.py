@@ -52,14 +52,17 @@ def test_synthetic_cfg2_cfg3(jit):
     _run(seqs, "TTAGGG", right_edge=True, jit=jit, label="fwd right edge")
 
 
-def test_iupac_reads_take_the_4bit_path():
+@pytest.mark.parametrize("jit", [False, True])
+def test_iupac_reads_take_the_4bit_path(jit):
+    """Reads with N: four nibble planes, scanned by ntl_scan_kernel<4> (jit=False) or by the NVRTC build ntl_scan_jit4."""
     from nanotel_b200 import READ_IUPAC
     from nanotel_b200.synth import as_list, synth_reads
     buf, off, meta = synth_reads(120, seed=7, median_len=3000, max_len=20000, telomeric_frac=0.5, n_frac=0.5)
     seqs = as_list(buf, off)
-    res = _run(seqs, "YYAGGG", rc=True, label="N reads")
+    res = _run(seqs, "YYAGGG", rc=True, jit=jit, label="N reads")
     assert (res["status"] & READ_IUPAC).any()
-    _run(seqs, "TTAGGG", tvr="TTGGG", label="N reads fixed")
+    _run(seqs, "TTAGGG", tvr="TTGGG", jit=jit, label="N reads fixed")
+    _run(seqs, "TTAGGG CCCTAA", tvr="TTGGG CCAGGG TCAGGG", jit=jit, label="N reads, two lengths")
 
 
 def test_short_and_ragged_reads():
