@@ -698,6 +698,7 @@ extern "C" int ntl_batch_enqueue(ntl_ctx *c)
         if (c->jit) {
             cudaError_t e = ntl_jit_launch(c->jit, &sa, 1, c->scan_grid4, c->stream);
             if (e != cudaSuccess) return fail(c, NTL_ERR_CUDA, "JIT scan kernel (IUPAC reads) launch failed: %s", cudaGetErrorString(e));
+            c->tm.scan_is_jit = 1;
         } else {
             CK(c, ntl_k_scan(&sa, 1, c->scan_grid, c->stream));
         }

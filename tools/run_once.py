@@ -14,8 +14,9 @@ ap.add_argument("--runs", type=int, default=4)
 ap.add_argument("--tvr", default=None)
 ap.add_argument("--patterns", default="YYAGGG")
 ap.add_argument("--no-jit", action="store_true")
+ap.add_argument("--n-frac", type=float, default=None, help="fraction of reads that carry N (they take the 4-bit path)")
 a = ap.parse_args()
-buf, off, meta = synth_reads(a.reads, 20261020)
+buf, off, meta = synth_reads(a.reads, 20261020, **({} if a.n_frac is None else {"n_frac": a.n_frac}))
 sc = Scanner(a.patterns, a.tvr, rc=True, jit=False if a.no_jit else None)
 sc.pack_concat(buf, off)
 sc.upload()
