@@ -160,3 +160,18 @@ def test_range_list_kind_follows_the_reference():
     n_list = O.analyze_read(O.make_params("TTAGGG TTAGGG"), seq).rec["t"][0]["n_ranges"]
     n_iupac = O.analyze_read(O.make_params("YYAGGG"), seq).rec["t"][0]["n_ranges"]
     assert n_raw == 492 and n_list < 20 and n_iupac < 20          # 492 raw hits vs a few merged runs
+
+
+def test_oracle_results_did_not_change_silently():
+    """Regression digest of the oracle's own output on seeded synthetic reads (tests/golden/make_oracle_regression.py):
+    seven configurations that exercise what the reference's artefacts do not pin.  Not a parity claim -- a tripwire."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_oracle_regression", os.path.join(GOLD, "make_oracle_regression.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    fx = json.load(open(os.path.join(GOLD, "oracle_regression.json")))
+    seqs = m.reads()
+    assert len(fx["configs"]) == len(m.CONFIGS)
+    for entry in fx["configs"]:
+        d, kept = m.digest(entry["config"], seqs)
+        assert (d, kept) == (entry["sha256"], entry["kept"]), entry["config"]
