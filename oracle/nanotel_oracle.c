@@ -634,6 +634,19 @@ int32_t ntlo_match_pattern(const char *seq, int32_t len, const char *pat, int32_
     return n;
 }
 
+/* get_sub_density (NanoTel.R:449-468) on an explicit range list, for the worked example in its own comment
+ * (NanoTel.R:459-464): the same reduce / coverage-prefix / division code analyze_read uses. */
+double ntlo_sub_density_ranges(const int32_t *starts, const int32_t *ends, int32_t n, int32_t L, int32_t a, int32_t b)
+{
+    rlist r; rl_init(&r);
+    for (int32_t i = 0; i < n; i++) rl_push(&r, starts[i], ends[i]);
+    rl_reduce(&r);
+    int32_t *pre = build_cov_prefix(&r, L);
+    const double d = sub_density(pre, L, a, b);
+    free(pre); rl_free(&r);
+    return d;
+}
+
 /* ---------------------------------------------------------------- batch driver (CPU baseline), pthreads */
 typedef struct {
     const ntlo_params *p; const patset_t *ps; const char *const *seqs; const int32_t *lens; int32_t n;

@@ -80,6 +80,9 @@ void ntlo_revcomp(const char *in, int32_t len, char *out);
 int32_t ntlo_match_pattern(const char *seq, int32_t len, const char *pat, int32_t max_mismatch, int32_t fixed,
                            int32_t *starts, int32_t max_hits);
 
+/* get_sub_density (NanoTel.R:449-468) on an explicit range list (unit tests: the example at NanoTel.R:459-464). */
+double ntlo_sub_density_ranges(const int32_t *starts, const int32_t *ends, int32_t n, int32_t L, int32_t a, int32_t b);
+
 /* Batch driver: analyse n reads with n_threads OpenMP threads (CPU baseline).
  * do_rc / use_filter follow NanoTel.R:2219-2232.  pass[i] = 0 if the read was filtered out.
  * win_off (n+1 entries, may be NULL) gives the per-read offset into win_counts, laid out

@@ -92,6 +92,8 @@ def lib():
         L.ntlo_match_pattern.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_int32]
         L.ntlo_match_pattern.restype = C.c_int32
+        L.ntlo_sub_density_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        L.ntlo_sub_density_ranges.restype = C.c_double
         L.ntlo_scan_batch.argtypes = [C.POINTER(Params), C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.ntlo_scan_batch.restype = C.c_int
@@ -152,6 +154,13 @@ def match_pattern(seq: bytes, pat: str, max_mismatch: int = 0, fixed: bool = Tru
     if n < 0:
         raise ValueError("bad pattern or sequence")
     return st[:n].copy()
+
+
+def sub_density_ranges(starts, ends, L: int, a: int, b: int) -> float:
+    """get_sub_density(IRanges(a, b), IRanges(starts, ends)) on a subject of length L (NanoTel.R:449-468)."""
+    st = np.ascontiguousarray(starts, np.int32)
+    en = np.ascontiguousarray(ends, np.int32)
+    return float(lib().ntlo_sub_density_ranges(st.ctypes.data, en.ctypes.data, len(st), L, a, b))
 
 
 def filter_read(P: Params, seq: bytes) -> bool:

@@ -213,6 +213,8 @@ struct ntl_reader {
     char err[512] = "";
 
     Chunk cur, next;
+    Chunk left;                     /* records read ahead with another nrec and not handed out yet */
+    int32_t left_pos = 0;
     std::thread worker;
     bool prefetching = false;
     int32_t prefetch_nrec = 0;
@@ -249,9 +251,33 @@ struct ntl_reader {
         bt_rec += k;
         return k;
     }
+    /* records [from, from + k) of src appended to c */
+    static void append(Chunk &c, const Chunk &src, int32_t from, int32_t k)
+    {
+        const int64_t s0 = src.seq_off[from], s1 = src.seq_off[from + k];
+        const int64_t m0 = src.name_off[from], m1 = src.name_off[from + k];
+        const int64_t sb = (int64_t)c.seq.size() - s0, mb = (int64_t)c.names.size() - m0;
+        c.seq.insert(c.seq.end(), src.seq.begin() + s0, src.seq.begin() + s1);
+        c.names.insert(c.names.end(), src.names.begin() + m0, src.names.begin() + m1);
+        for (int32_t i = 1; i <= k; i++) {
+            c.seq_off.push_back(src.seq_off[from + i] + sb);
+            c.name_off.push_back(src.name_off[from + i] + mb);
+        }
+        c.n += k;
+    }
+    void take_left(Chunk &c, int32_t k) { append(c, left, left_pos, k); left_pos += k; }
     void read_chunk(Chunk &c, int32_t nrec)
     {
         c.clear();
+        if (left_pos < left.n) {                         /* never drop parsed records: they come first */
+            const int32_t avail = left.n - left_pos;
+            take_left(c, nrec > 0 ? std::min(nrec, avail) : avail);
+            if (left_pos >= left.n) {
+                const int st = left.status;
+                left.clear(); left_pos = 0;
+                if (st < 0) { c.status = st; return; }   /* the read-ahead ended in an error: report it after its records */
+            }
+        }
         while (nrec <= 0 || c.n < nrec) {
             const int r = take(c, nrec > 0 ? nrec - c.n : 0);
             if (r < 0) { c.status = r; return; }
@@ -289,7 +315,20 @@ extern "C" int32_t ntl_reader_next(ntl_reader *r, int32_t nrec, const char **seq
         r->prefetching = false;
         std::swap(r->cur, r->next);
     } else {
-        if (r->prefetching) { r->worker.join(); r->prefetching = false; }   /* nrec changed: cannot happen in NanoTel */
+        if (r->prefetching) {
+            /* nrec changed (NanoTel.R never does that, the ABI allows it): nothing that was parsed is dropped.  The
+             * chunk read ahead with the old size comes first (it was filled from `left`, then from the files), then
+             * whatever `left` still holds; read_chunk splits or tops that up to the new size. */
+            r->worker.join();
+            r->prefetching = false;
+            Chunk m; m.clear();
+            if (r->next.n > 0) ntl_reader::append(m, r->next, 0, r->next.n);
+            if (r->left_pos < r->left.n) ntl_reader::append(m, r->left, r->left_pos, r->left.n - r->left_pos);
+            m.status = r->next.status < 0 ? r->next.status : r->left.status;
+            std::swap(r->left, m);
+            r->left_pos = 0;
+            r->next.clear();
+        }
         r->read_chunk(r->cur, nrec);
     }
     if (r->cur.status < 0) return r->cur.status;

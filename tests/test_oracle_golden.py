@@ -6,6 +6,8 @@
 * single_read_plots_adj/read1.eps ... read4.eps: the per-window density vectors of all four reads, tracks A and B
   (987 windows x 2 tracks; for reads 2-4 the integer covered counts follow exactly).
 * the matchPattern example written in NanoTel.R:273-302 (right-hand out-of-bounds hit and trim()).
+* the get_sub_density example written in NanoTel.R:459-464 (8/21).
+* Example/Example_output/log/run.log:20-46 (summary() quartiles) and the subtitles of read1-4.eps.
 Everything after NanoTel.R:1126 has no golden data anywhere: tested below only as restatement regression values
 (an independent throw-away restatement) and marked as such.
 """
@@ -77,6 +79,42 @@ def test_eps_window_densities_of_reads_2_to_4(example_reads, k):
         scale = x[n + 1] / (len(seq) - 1)
         np.testing.assert_allclose(x[1:n + 1], (st - 1) * scale, atol=0.6)
         assert abs(x[n + 2] - x[n + 1]) < 0.02
+
+
+def test_get_sub_density_worked_example_from_the_reference_comments():
+    # NanoTel.R:459-464: sub_irange = (10, 30), ranges = {(2,8), (16,21), (29,56)} -> intersect {(16,21), (29,30)}
+    # -> width 6 + 2 = 8, sub_irange width 21 -> density 8/21 ("# 0.38")
+    d = O.sub_density_ranges([2, 16, 29], [8, 21, 56], 60, 10, 30)
+    assert d == 8.0 / 21.0 and round(d, 2) == 0.38
+    # overlapping and adjacent ranges are merged before the intersect (IRanges::intersect normalises)
+    assert O.sub_density_ranges([2, 5, 9], [6, 8, 12], 20, 1, 20) == 11.0 / 20.0
+
+
+def _r_summary(x):
+    """R's summary() as NanoTel.R:2396-2427 logs it: quantile type 7 + mean, printed by format(digits = 4), which
+    never drops integer digits: values >= 1000 appear rounded to integers (sprintf rounding: half to even)."""
+    x = np.asarray(x, np.float64)
+    q = [x.min(), np.quantile(x, 0.25), np.quantile(x, 0.5), x.mean(), np.quantile(x, 0.75), x.max()]
+    return [float(round(v)) if v >= 1000 else float("%.4g" % v) for v in q]
+
+
+def test_run_log_quartiles_and_eps_subtitles(example_reads):
+    """Example_output/log/run.log:20-46 (summary() of read length / telomere length / telomere length with one
+    mismatch) and the subtitle of every read<k>.eps, against the oracle at the stage the 2023 example was produced
+    with (acc_*, NanoTel.R:1126)."""
+    fx = json.load(open(os.path.join(GOLD, "example_log_and_subtitles.json")))
+    P = O.make_params("TTAGGG", None, 0.6, 100, False)
+    lens, tl, tlm = [], [], []
+    for k, (name, seq) in enumerate(example_reads, 1):
+        r = O.analyze_read(P, seq).rec
+        a = int(r["t"][0]["acc_end"]) - int(r["t"][0]["acc_start"]) + 1
+        b = int(r["t"][1]["acc_end"]) - int(r["t"][1]["acc_start"]) + 1
+        sub = fx["subtitles"][str(k)]
+        assert (len(seq), a, b) == (sub["read_length"], sub["telomere_length"], sub["telomere_length_mismatch"])
+        lens.append(len(seq)); tl.append(a); tlm.append(b)
+    assert _r_summary(lens) == fx["read_length"] == fx["telomeric_read_length"]
+    assert _r_summary(tl) == fx["telomere_length"]
+    assert _r_summary(tlm) == fx["telomere_length_mismatch"]
 
 
 def test_matchpattern_example_from_the_reference_comments():

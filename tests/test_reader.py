@@ -123,3 +123,46 @@ def test_file_thread_blocks_on_a_full_queue(tmp_path, monkeypatch):
     it = iter(NativeReader([str(big), str(small)], "fastq", 10))
     next(it)
     it.close()                                                          # the blocked file thread must let go
+
+
+def test_varying_nrec_never_drops_records(tmp_path):
+    """The ABI allows a different nrec on every ntl_reader_next call; the chunk read ahead with the previous size
+    must be handed out (split or topped up), never dropped."""
+    import ctypes as C
+    import gzip
+    from nanotel_b200 import _lib
+    rng = np.random.default_rng(5)
+    names, seqs = [], []
+    paths = []
+    for f in range(3):
+        p = tmp_path / ("v%d.fastq.gz" % f)
+        with gzip.open(p, "wb") as g:
+            for i in range(41):
+                s = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), int(rng.integers(1, 300))))
+                nm = "r%d_%d" % (f, i)
+                g.write(b"@" + nm.encode() + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n")
+                names.append(nm); seqs.append(s)
+        paths.append(str(p))
+    L = _lib.load()
+    arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+    h = C.c_void_p()
+    assert L.ntl_reader_open(C.byref(h), arr, len(paths), b"fastq") == 0
+    sizes = [5, 1, 17, 3, 3, 40, 2, 9, 1000]
+    got_names, got_seqs, k = [], [], 0
+    sb, so, nb, no = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    while True:
+        nrec = sizes[k % len(sizes)]; k += 1
+        n = L.ntl_reader_next(h, nrec, C.byref(sb), C.byref(so), C.byref(nb), C.byref(no))
+        assert n >= 0
+        if n == 0:
+            break
+        assert n <= nrec
+        soff = np.ctypeslib.as_array(C.cast(so, C.POINTER(C.c_int64)), (n + 1,))
+        noff = np.ctypeslib.as_array(C.cast(no, C.POINTER(C.c_int64)), (n + 1,))
+        sraw = C.string_at(sb, int(soff[-1]))
+        nraw = C.string_at(nb, int(noff[-1]))
+        for i in range(n):
+            got_seqs.append(sraw[int(soff[i]):int(soff[i + 1])])
+            got_names.append(nraw[int(noff[i]):int(noff[i + 1])].decode())
+    L.ntl_reader_close(h)
+    assert got_names == names and got_seqs == seqs
