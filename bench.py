@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=50000, help="reads of the CPU-baseline sample")
     ap.add_argument("--no-jit", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full oracle comparison of the timed workload")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -279,6 +280,15 @@ def main():
     prepacked_s = (time.perf_counter() - t0) / args.e2e_steps
     clocks = sampler.stop() if sampler else None
 
+    # -- parity verdict on the timed workload (outside every timed region; rank 0's shard): every per-read record and
+    #    every window count of the batch that is resident right now against the oracle (TEST INFRASTRUCTURE as checker)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle.compare import full_parity
+        res_p = sc.download()
+        parity = full_parity(sc, res_p, (buf, offsets), patterns, tvr, 0.6, S, right_edge, rc, use_filter,
+                             n_threads=cores)
+
     # -- max over ranks
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
     b = torch.tensor([float(bases)], dtype=torch.float64, device="cuda")
@@ -317,6 +327,7 @@ def main():
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "clocks": clocks, "telomeric_reads_found_rank0": n_keep, "bases_per_gpu": bases,
             "locate_candidates_rank0": int(tm["candidates"]),
+            "parity": parity,
         }
         if not args.no_cpu_baseline:
             v, sb, sn, dt = cpu_baseline(buf, offsets, wl, args.cpu_sample, cores)

@@ -155,6 +155,11 @@ void *ntl_stream(const ntl_ctx *ctx);     /* cudaStream_t the kernels are launch
  * this call (one small synchronous copy), until the next batch replaces it. */
 int ntl_get_windows(const ntl_ctx *ctx, int32_t read_idx, int32_t track, int32_t cap,
                     int32_t *start_index, int32_t *end_index, int32_t *covered, double *density);
+/* Bulk form for whole-batch comparisons (parity checks at BASELINE sizes): the covered-base counts of `track` for
+ * EVERY read of the last batch, read after read in input order, n_win entries per read (results[i].n_win; window
+ * order; no padding), fetched from the device in one copy.  Entries of filtered reads are undefined.  Returns the
+ * total number of entries (the sum of n_win) or a negative ntl_status; writes nothing beyond cap entries. */
+int64_t ntl_get_window_counts(const ntl_ctx *ctx, int32_t track, uint16_t *out, int64_t cap);
 /* NTL_OPT_DEBUG_STAGES only: intermediate intervals of read read_idx, track. */
 int ntl_get_stages(const ntl_ctx *ctx, int32_t read_idx, int32_t track, ntl_stage *out);
 

@@ -880,6 +880,31 @@ extern "C" int ntl_get_windows(const ntl_ctx *c, int32_t read_idx, int32_t track
     return n;
 }
 
+extern "C" int64_t ntl_get_window_counts(const ntl_ctx *c, int32_t track, uint16_t *out, int64_t cap)
+{
+    if (!c) return NTL_ERR_ARG;
+    ntl_ctx *mc = const_cast<ntl_ctx *>(c);
+    if (c->state < ST_DOWNLOADED) return fail(mc, NTL_ERR_STATE, "ntl_get_window_counts before the batch was downloaded");
+    if (track < 0 || track >= c->dev.n_tracks || (!out && cap > 0)) return fail(mc, NTL_ERR_ARG, "ntl_get_window_counts: bad arguments");
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(mc, NTL_ERR_CUDA, "cudaSetDevice failed");
+    std::vector<uint16_t> raw((size_t)c->total_windows + 8);
+    if (c->total_windows > 0) {
+        const uint16_t *src = (const uint16_t *)c->d_cum.p + (size_t)track * c->total_windows;
+        cudaError_t e = cudaMemcpyAsync(raw.data(), src, (size_t)c->total_windows * 2, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return fail(mc, NTL_ERR_CUDA, "ntl_get_window_counts: %s", cudaGetErrorString(e));
+    }
+    const ntl_read_result *res = (const ntl_read_result *)c->h_results.p;
+    int64_t pos = 0;
+    for (int32_t i = 0; i < c->n_reads; i++) {
+        const int32_t n = res[i].n_win;
+        const uint16_t *cum = raw.data() + res[i].win_offset;
+        for (int32_t k = 0; k < n; k++, pos++)
+            if (pos < cap) out[pos] = (uint16_t)(cum[k] - (k ? cum[k - 1] : 0));
+    }
+    return pos;
+}
+
 extern "C" int ntl_get_stages(const ntl_ctx *c, int32_t read_idx, int32_t track, ntl_stage *out)
 {
     if (!c || !out) return NTL_ERR_ARG;

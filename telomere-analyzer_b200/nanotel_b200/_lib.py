@@ -56,7 +56,7 @@ assert RESULT_DTYPE.itemsize == 64
 EXPORTS = [
     "ntl_version", "ntl_create", "ntl_destroy", "ntl_last_error", "ntl_scan_batch", "ntl_scan_batch_concat",
     "ntl_batch_pack", "ntl_batch_upload", "ntl_batch_run", "ntl_batch_enqueue", "ntl_batch_wait", "ntl_batch_download", "ntl_get_timings", "ntl_stream",
-    "ntl_get_windows", "ntl_get_stages", "ntl_jit_compile_check", "ntl_pack_read", "ntl_assign_serials", "ntl_count_windows",
+    "ntl_get_windows", "ntl_get_window_counts", "ntl_get_stages", "ntl_jit_compile_check", "ntl_pack_read", "ntl_assign_serials", "ntl_count_windows",
     "ntl_reader_open", "ntl_reader_next", "ntl_reader_error", "ntl_reader_close",
 ]
 
@@ -92,6 +92,8 @@ def load() -> C.CDLL:
     L.ntl_stream.argtypes = [vp]
     L.ntl_stream.restype = vp
     L.ntl_get_windows.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
+    L.ntl_get_window_counts.argtypes = [vp, i32, vp, i64]
+    L.ntl_get_window_counts.restype = i64
     L.ntl_get_stages.argtypes = [vp, i32, i32, C.POINTER(Stage)]
     L.ntl_jit_compile_check.argtypes = [C.POINTER(Params), C.c_char_p, C.c_char_p, C.c_int, C.c_char_p]
     L.ntl_jit_compile_check.restype = C.c_long

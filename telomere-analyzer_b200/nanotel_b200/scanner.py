@@ -185,6 +185,19 @@ class Scanner:
             self._check(r)
         return st[:n_win], en[:n_win], cov[:n_win], den[:n_win]
 
+    def window_counts(self, track: int, total: Optional[int] = None) -> np.ndarray:
+        """ntl_get_window_counts: covered counts of every window of every read of the last batch (uint16, read after
+        read, n_win entries each) -- the bulk form of windows() for whole-batch comparisons."""
+        if total is None:
+            total = self._L.ntl_get_window_counts(self._h, track, None, 0)
+            if total < 0:
+                self._check(int(total))
+        out = np.zeros(max(int(total), 1), np.uint16)
+        r = self._L.ntl_get_window_counts(self._h, track, out.ctypes.data, int(total))
+        if r < 0:
+            self._check(int(r))
+        return out[:int(total)]
+
     def stages(self, read_idx: int, track: int) -> dict:
         s = _lib.Stage()
         self._check(self._L.ntl_get_stages(self._h, read_idx, track, C.byref(s)))
