@@ -34,26 +34,33 @@
 extern "C" {
 #endif
 
-#define NTL_VERSION 100          /* 0.1.0 */
+#define NTL_VERSION 200          /* 0.2.0 */
 #define NTL_MAX_PATTERNS 16      /* per list (--patterns, --tvr_patterns)                         */
 #define NTL_MAX_PATLEN   18      /* NanoTel.R:589,647: assert(str_length(pattern) <= subseq_width) */
+#define NTL_MAX_DEVICES  16      /* GPUs of one box a context may shard its batches over            */
+#define NTL_MAX_SUBSEQ   43690   /* --subseq_length: the merged last window (up to S + ceil(S/2) - 1 wide) must fit 16 bits */
 
 typedef enum {
     NTL_OK = 0,
-    NTL_ERR_ARG = -1,            /* NULL pointer, bad count, subseq_length out of [1, 65535]       */
+    NTL_ERR_ARG = -1,            /* NULL pointer, bad count, subseq_length out of [1, NTL_MAX_SUBSEQ] */
     NTL_ERR_PATTERN = -2,        /* empty pattern, > 18 nt, letter outside the IUPAC DNA alphabet  */
-    NTL_ERR_SEQUENCE = -3,       /* zero-length read (NanoTel.R:216 stops) or non-DNA letter       */
+    NTL_ERR_SEQUENCE = -3,       /* a letter outside the Biostrings DNA alphabet, read > 2^30 bases */
     NTL_ERR_CUDA = -4,           /* no device / CUDA runtime error (message has the CUDA string)   */
     NTL_ERR_NOMEM = -5,
-    NTL_ERR_JIT = -6,            /* NVRTC specialisation failed and NTL_OPT_REQUIRE_JIT was set    */
+    NTL_ERR_JIT = -6,            /* no specialised scan kernel (precompiled / cached / NVRTC) and NTL_OPT_REQUIRE_JIT was set */
     NTL_ERR_STATE = -7           /* call order violated (e.g. ntl_batch_run before ntl_batch_pack) */
 } ntl_status;
 
 /* ntl_params.options */
-#define NTL_OPT_NO_JIT        1u  /* use the precompiled runtime-pattern scan kernel only           */
-#define NTL_OPT_REQUIRE_JIT   2u  /* fail ntl_create if the NVRTC-specialised kernel cannot be built */
+#define NTL_OPT_NO_JIT        1u  /* use the generic (runtime-pattern) scan kernel only              */
+#define NTL_OPT_REQUIRE_JIT   2u  /* fail ntl_create if no specialised scan kernel can be had        */
 #define NTL_OPT_DEBUG_STAGES  4u  /* also record the intermediate intervals (ntl_get_stages)         */
-#define NTL_OPT_DEVICE_PACK   8u  /* upload ASCII and pack on the GPU instead of packing on the host */
+
+/* ntl_scan_path(): where the scan kernel of a context comes from */
+#define NTL_SCAN_GENERIC      0   /* generic kernel: any patterns / subseq_length, several times slower (see ntl_scan_path_note) */
+#define NTL_SCAN_PRECOMPILED  1   /* specialised, cubin built ahead of time next to the library (no NVRTC needed) */
+#define NTL_SCAN_CACHED       2   /* specialised, from the per-user cubin cache                                    */
+#define NTL_SCAN_NVRTC        3   /* specialised, compiled by NVRTC in ntl_create                                  */
 
 typedef struct {
     int32_t n_patterns;                 /* --patterns tokens in CLI order (NanoTel.R:2322-2326); 1 token = scalar */
@@ -61,14 +68,17 @@ typedef struct {
     int32_t n_tvr;                      /* --tvr_patterns tokens (0 = NULL, NanoTel.R:2328-2334)                   */
     const char *const *tvr_patterns;
     double  min_density;                /* --min_density   (NanoTel.R:2337)                                        */
-    int32_t subseq_length;              /* --subseq_length (NanoTel.R:2338), 1..65535                              */
+    int32_t subseq_length;              /* --subseq_length (NanoTel.R:2338), 1..NTL_MAX_SUBSEQ                     */
     int32_t rc;                         /* --rc: scan the reverse complement of every read (NanoTel.R:2219-2221)   */
     int32_t use_filter;                 /* --use_filter (NanoTel.R:2227-2232)                                      */
     int32_t right_edge;                 /* --check_right_edge (NanoTel.R:2394 right_edge =)                        */
-    int32_t device;                     /* CUDA device ordinal                                                     */
+    int32_t device;                     /* CUDA device ordinal (used when n_devices == 0)                          */
     uint32_t options;                   /* NTL_OPT_*                                                               */
-    int32_t host_threads;               /* packer threads; 0 = number of online CPUs (capped at 64)                */
-    int32_t reserved;
+    int32_t host_threads;               /* packer threads in total; 0 = number of online CPUs                      */
+    int32_t n_devices;                  /* > 0: shard every batch over device_ids[0 .. n_devices) -- what replaces the
+                                           8 forked workers of NanoTel.R:2207, :2234-2254: contiguous shards balanced by
+                                           bases, one per GPU, records gathered in input order; no collective         */
+    const int32_t *device_ids;
 } ntl_params;
 
 /* ntl_read_result.status bits */
@@ -88,7 +98,7 @@ typedef struct {        /* 64 bytes, one per read, input order */
     int32_t status;     /* NTL_READ_* bits */
     int32_t n_win;      /* rows of the window table (split_telo, NanoTel.R:199-227) */
     ntl_track track[3]; /* 0: exact, 1: one mismatch, 2: one mismatch + TVR (valid only if n_tvr > 0) */
-    int64_t win_offset; /* first window of this read inside the batch's window arrays */
+    int64_t win_offset; /* first count block of this read inside its device's count planes (internal) */
 } ntl_read_result;
 
 typedef struct {        /* NTL_OPT_DEBUG_STAGES: one per read and track, mirrors the oracle's stages */
@@ -104,15 +114,15 @@ typedef struct {        /* wall/device times of the last batch, milliseconds */
     double filter_ms;       /* device: edge-filter kernel                                                    */
     double scan_ms;         /* device: match + coverage + window-prefix kernel(s)  (the dominant kernel)     */
     double locate_ms;       /* device: triage + per-read locator / refinement kernels                        */
-    double triage_ms;       /* device: the triage kernel alone, FIRST pass only (not a sum; part of locate_ms) */
+    double triage_ms;       /* device: the triage kernel alone (part of locate_ms)                           */
     double d2h_ms;          /* device: results + window prefixes download                                    */
     double total_ms;        /* host wall clock of the whole ntl_scan_batch call                              */
     int64_t bases;          /* bases in the batch                                                            */
     int64_t packed_bytes;   /* bytes of packed reads resident on the device                                  */
-    int64_t window_bytes;   /* bytes of per-window prefix counts written by the scan kernel                  */
+    int64_t window_bytes;   /* bytes of per-block covered counts written by the scan kernel                  */
     int64_t h2d_bytes, d2h_bytes;
     int32_t kernel_launches;/* kernels launched by the passes the last ntl_batch_wait covered                */
-    int32_t scan_is_jit;    /* 1 if the NVRTC-specialised scan kernel ran                                    */
+    int32_t scan_is_jit;    /* 1 if the specialised span scan kernel ran (0: the generic kernel)             */
     int32_t steps;          /* passes covered by filter_ms / scan_ms / locate_ms (sums over those passes)    */
     int32_t candidates;     /* reads of the last pass that needed the full locate kernel (the rest ended in triage) */
 } ntl_timings;
@@ -126,6 +136,17 @@ int  ntl_create(ntl_ctx **ctx, const ntl_params *params);
 void ntl_destroy(ntl_ctx *ctx);
 /* ctx may be NULL: returns the message of the last failed ntl_create on this thread. */
 const char *ntl_last_error(const ntl_ctx *ctx);
+/* Which scan kernel the context runs (NTL_SCAN_*), and why when it is the generic one ("" otherwise).  A context
+ * that had to fall back to the generic kernel also prints one warning line on stderr in ntl_create. */
+int  ntl_scan_path(const ntl_ctx *ctx);
+const char *ntl_scan_path_note(const ntl_ctx *ctx);
+int  ntl_device_count(const ntl_ctx *ctx);
+/* Shards of the last batch: bounds[0 .. n + 1) (read indices) and devices[0 .. n); returns the number of shards. */
+int  ntl_get_shards(const ntl_ctx *ctx, int32_t *bounds, int32_t *devices, int32_t cap);
+/* The span geometry chosen for --subseq_length (telomere-analyzer_b200/csrc/ntl_dev.h): positions per count block,
+ * blocks per window, position words per span, blocks per span (0 = generic layout). */
+int  ntl_get_geometry(const ntl_ctx *ctx, int32_t *block, int32_t *blocks_per_window, int32_t *words_per_span,
+                      int32_t *blocks_per_span);
 
 /* -- one --nrec chunk, host buffers in, host results out (replaces NanoTel.R:2219-2254) --------------------- */
 /* seq[i] points at len[i] ASCII letters (no terminator needed).  *results stays valid until the next batch call
@@ -135,6 +156,11 @@ int ntl_scan_batch(ntl_ctx *ctx, const char *const *seq, const int64_t *len, int
 /* Same, reads given as one concatenated buffer: read i = buf[offsets[i] .. offsets[i+1]). */
 int ntl_scan_batch_concat(ntl_ctx *ctx, const char *buf, const int64_t *offsets, int32_t n_reads,
                           const ntl_read_result **results);
+/* Same, reads given the way an XStringSet holds them (the dna_reads of NanoTel.R:2213, no as.character() copy): one
+ * pool of bytes + 1-based start + width per read.  biostrings_codes != 0: the pool holds Biostrings' DNA byte codes
+ * (A 1, C 2, G 4, T 8, IUPAC letters = OR of those bits, '-' 16, '+' 32, '.' 64), else ASCII. */
+int ntl_scan_batch_pool(ntl_ctx *ctx, const unsigned char *pool, const int32_t *start, const int32_t *width,
+                        int32_t n_reads, int32_t biostrings_codes, const ntl_read_result **results);
 
 /* -- the same path in stages (used by bench.py to time the device-resident part; same results) ------------- */
 int ntl_batch_pack(ntl_ctx *ctx, const char *const *seq, const int64_t *len, int32_t n_reads);
@@ -182,9 +208,15 @@ void ntl_reader_close(ntl_reader *reader);
  * write the cubin to cubin_path (for cuobjdump).  Returns the cubin size in bytes or a negative ntl_status. */
 long ntl_jit_compile_check(const ntl_params *params, const char *arch, char *log, int log_cap,
                            const char *cubin_path);
-/* Pack ONE read exactly as ntl_batch_pack does (no device needed): writes the quads to `words` (capacity in
- * 32-bit words) and returns the number of words written, negative on error; *four_bit = 1 if the read holds a
- * letter other than A/C/G/T and was packed as four planes.  Layout: telomere-analyzer_b200/csrc/ntl_dev.h. */
+/* The same, stored as <dir>/<key>.cubin in the format ntl_create looks for in <library directory>/precompiled
+ * (build.py calls this for the default pattern sets, so that they need neither NVRTC nor a CUDA toolkit at run time). */
+long ntl_jit_precompile_to(const ntl_params *params, const char *arch, const char *dir, char *log, int log_cap);
+/* The generated source of the specialised kernel (prologue of constants + #include "ntl_scan.cuh"); returns its
+ * length.  Used by the CPU tests, which compile the same text as a host model. */
+long ntl_jit_get_source(const ntl_params *params, char *buf, long cap);
+/* Pack ONE read exactly as ntl_batch_pack does (no device needed): writes its position words ({lo, hi} per 32
+ * positions, or {A, C, G, T} if the read holds a letter other than A/C/G/T: *four_bit = 1) to `words` (capacity in
+ * 32-bit words) and returns the number of words written, negative on error.  Layout: csrc/ntl_dev.h. */
 long ntl_pack_read(const char *seq, int64_t len, int32_t rc, uint32_t *words, int64_t capacity, int32_t *four_bit);
 
 /* -- host-side helpers of the same path ------------------------------------------------------------------- */

@@ -1,36 +1,56 @@
 /*
- * ntl_kernels.cu -- sm_100a kernels of libnanotel_b200 other than the JIT-specialised scan:
- *   K2  ntl_scan_kernel<2|4>   runtime-pattern build of ntl_scan.cuh (any pattern set; 4-plane build for IUPAC reads)
- *   K4  ntl_filter_kernel      --use_filter edge filter            (filter_reads/filter_density, NanoTel.R:2083-2163)
+ * ntl_kernels.cu -- sm_100a kernels of libnanotel_b200 other than the compile-time-specialised span scan (ntl_scan.cuh):
+ *   K2g ntl_scan_generic_kernel  any pattern set / any subseq_length, patterns in __constant__ memory: the path taken
+ *                              when no specialised build exists (NTL_OPT_NO_JIT, no NVRTC and no precompiled cubin,
+ *                              or a subseq_length without a span geometry); one warp per read, block counts by atomics
+ *   K4  ntl_filter_kernel      --use_filter edge filter            (filter_reads/filter_density, NanoTel.R:2083-2163);
+ *                              also marks the spans / work items of the reads it keeps for the span scan
+ *       ntl_items_kernel       compacts the marked work items into the list the span scan walks
  *   K3a ntl_triage_kernel      eight lanes per read: proves that a read has no telomeric window on any track and no
  *                              hit in its first 18 bases and writes its (trivial) record, or hands it to K3b
  *   K3b ntl_locate_kernel      one warp per (candidate read, track): locator and refinement (find_telo_position_wraper
  *                              NanoTel.R:1080-1155 and everything it calls, analyze_read's densities and keep rule
  *                              :1840-1868)
- *       ntl_gather_windows_kernel   window prefixes of the kept reads, packed for the device-to-host copy
+ *       ntl_gather_windows_kernel   block counts of the kept reads, packed for the device-to-host copy
  *
  * Control flow inside a team / warp is uniform.  Where the reference consults its range list (get_accurate_start/end,
  * get_sub_density on arbitrary intervals) K3b re-derives hits and coverage locally from the packed read -- one word
- * (32 positions) per lane, the same bit-parallel matching as K2 -- so that K2 never has to spill per-base masks to
- * HBM.  All fp64 expressions are written exactly as NanoTel.R evaluates them (int/int divisions in double, sums in
- * window order); this file must be compiled with --fmad=false.
+ * (32 positions) per lane, bit-parallel -- so that K2 never has to spill per-base masks to HBM.  All fp64 expressions
+ * are written exactly as NanoTel.R evaluates them (int/int divisions in double, sums in window order); this file must
+ * be compiled with --fmad=false.
+ *
+ * Positions: K3/K4 address a read through VIRTUAL words whose bit b holds position 32 w + b (1-based position =
+ * bit index, bit 0 of word 0 is a pad), i.e. the packed stream (position p = bit p - 1, ntl_dev.h) shifted up by one
+ * bit on the fly (rv_word); that keeps every interval computation below in the reference's 1-based coordinates.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "ntl_dev.h"
 #include "../../include/nanotel_b200.h"
 
+typedef unsigned int u32;
+#define NTL_FULL 0xffffffffu
+
 __constant__ ntl_dev_params c_prm;
 
-#include "ntl_scan.cuh"
-
-/* =============================================================================================================
- * K2 (runtime-pattern build)
- * ============================================================================================================= */
-template <int NPL>
-__global__ void __launch_bounds__(256) ntl_scan_kernel(const ntl_scan_args a)
+__device__ __forceinline__ int ntl_nwin(int L, int S)
 {
-    ntl_scan_body<NPL>(a);
+    /* split_telo, NanoTel.R:216-224: drop the last window if  L - last_start < S / 2  (real division) */
+    int n = (L - 1) / S + 1;
+    int last = 1 + (n - 1) * S;
+    if (2 * (L - last) < S) n -= 1;
+    return n;
+}
+
+/* bits b of the virtual word starting at bit index wpos with 1 <= wpos + b <= L: the low  clamp(L - wpos + 1, 0, 32)
+ * bits (one clamped funnel shift), minus bit 0 of the read's very first word (the pad position) */
+__device__ __forceinline__ u32 ntl_valid_word(int wpos, int L)
+{
+    int nb = L - wpos + 1;
+    if (nb < 0) nb = 0;
+    u32 m = __funnelshift_lc(NTL_FULL, 0u, nb);
+    if (wpos == 0) m &= ~1u;
+    return m;
 }
 
 /* =============================================================================================================
@@ -41,10 +61,11 @@ __global__ void __launch_bounds__(256) ntl_scan_kernel(const ntl_scan_args a)
 #define NTL_IMAX 2147483647
 
 struct ReadView {
-    const u32 *base;
+    const u32 *base;  /* record of the read's position word 0: {lo, hi} (fmt 0) or {A, C, G, T} (fmt 1) per word */
     int L;
-    int fmt;        /* 0: 2-bit quads of 8 words, 1: 4-bit quads of 16 words */
-    int n_words;
+    int fmt;        /* 0: 2-bit records of 2 words, 1: 4-bit records of 4 words */
+    int n_words;    /* virtual words: (L >> 5) + 1 */
+    int n_raw;      /* position words that hold letters: (L + 31) >> 5 */
     /* locate kernel only: the two coverage blocks (one word per lane, warp_cov) that get_accurate_start / _end
      * computed for this (read, track), kept in shared memory so that the partial windows of the final density are
      * not derived from the read a second time.  ccov[slot * 32 + lane], cwb[slot] = first word or NTL_NONE. */
@@ -52,11 +73,25 @@ struct ReadView {
     int *cwb;
 };
 
+__device__ __forceinline__ void rv_init(ReadView &rv, const ntl_read_args &a, int r)
+{
+    rv.L = a.len[r]; rv.fmt = a.fmt[r];
+    rv.base = rv.fmt ? a.arena4 + (size_t)a.woff[r] * 4 : a.arena2 + (size_t)a.woff[r] * 2;
+    rv.n_words = (rv.L >> 5) + 1; rv.n_raw = (rv.L + 31) >> 5;
+    rv.ccov = nullptr; rv.cwb = nullptr;
+}
+
+__device__ __forceinline__ u32 rv_raw(const ReadView &rv, int plane, int x)
+{
+    if (x < 0 || x >= rv.n_raw) return 0u;
+    return rv.fmt ? rv.base[(size_t)x * 4 + plane] : rv.base[(size_t)x * 2 + plane];
+}
+
+/* virtual word w of a plane: bit b = position 32 w + b */
 __device__ __forceinline__ u32 rv_word(const ReadView &rv, int plane, int w)
 {
     if (w < 0 || w >= rv.n_words) return 0u;
-    const int q = w >> 2, i = w & 3;
-    return rv.fmt ? rv.base[(size_t)q * 16 + plane * 4 + i] : rv.base[(size_t)q * 8 + plane * 4 + i];
+    return __funnelshift_l(rv_raw(rv, plane, w - 1), rv_raw(rv, plane, w), 1);
 }
 
 /* One-hot (ACGT reads) or IUPAC (4-bit reads) planes A, C, G, T for the 32 positions p .. p+31, zeroed outside
@@ -110,13 +145,12 @@ __device__ __forceinline__ void word_planes(const ReadView &rv, int w, u32 (&pl)
 {
     if (w < 0 || w >= rv.n_words) { pl[0] = pl[1] = pl[2] = pl[3] = 0u; return; }
     const u32 vm = ntl_valid_word(w << 5, rv.L);
-    const int q = w >> 2, i = w & 3;
     if (rv.fmt == 0) {
-        const u32 lo = rv.base[(size_t)q * 8 + i], hi = rv.base[(size_t)q * 8 + 4 + i];
+        const u32 lo = rv_word(rv, 0, w), hi = rv_word(rv, 1, w);
         pl[0] = ~hi & ~lo & vm; pl[1] = ~hi & lo & vm; pl[2] = hi & lo & vm; pl[3] = hi & ~lo & vm;
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; k++) pl[k] = rv.base[(size_t)q * 16 + k * 4 + i] & vm;
+        for (int k = 0; k < 4; k++) pl[k] = rv_word(rv, k, w) & vm;
     }
 }
 
@@ -252,8 +286,7 @@ __global__ void __launch_bounds__(256) ntl_filter_kernel(const ntl_read_args a)
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     if (r >= a.n_reads) return;
     ReadView rv;
-    rv.L = a.len[r]; rv.fmt = a.fmt[r]; rv.base = a.packed + a.woff[r]; rv.n_words = (rv.L >> 5) + 1;
-    rv.ccov = nullptr; rv.cwb = nullptr;
+    rv_init(rv, a, r);
     int keep = 0;
     if (rv.L >= 1000) {                                         /* :2124 */
         int lo, hi;
@@ -293,6 +326,35 @@ __global__ void __launch_bounds__(256) ntl_filter_kernel(const ntl_read_args a)
         keep = total_density >= c_prm.filter_threshold ? 1 : 0;                  /* :2101, :2143 */
     }
     if (sub == 0) a.pass[r] = (uint8_t)keep;
+    /* the span scan walks spans, not reads: give this read's spans their verdict and, for a read that stays, mark the
+     * work items (groups of 32 spans) that hold them */
+    if (c_prm.BPS > 0 && a.span_flags[rv.fmt] != nullptr) {
+        const int W = c_prm.W;
+        const int64_t s0 = a.woff[r] / W;
+        const int nsp = (rv.L + 32 * W - 1) / (32 * W);
+        const int ltail = rv.L - (nsp - 1) * 32 * W;
+        const int tail_from = (nsp >= 2 && ltail < NTL_DEV_MAX_LEN) ? nsp - 2 : nsp - 1;
+        uint8_t *fl = a.span_flags[rv.fmt] + s0;
+        uint8_t *act = a.item_active[rv.fmt];
+        for (int s = sub; s < nsp; s += 8) {
+            fl[s] = (uint8_t)((s == 0 ? NTL_SPAN_FIRST : 0) | (s >= tail_from ? NTL_SPAN_TAIL : 0) | (keep ? 0 : NTL_SPAN_SKIP));
+            if (keep) act[(s0 + s) / NTL_ITEM_SPANS] = 1;
+        }
+    }
+}
+
+/* the work items the filter marked, as a list (order does not matter) */
+__global__ void __launch_bounds__(256) ntl_items_kernel(const uint8_t *active, int n_items, int32_t *items, u32 *counter)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const bool on = i < n_items && active[i] != 0;
+    const u32 m = __ballot_sync(NTL_FULL, on);
+    if (m == 0u) return;
+    int base = 0;
+    const int leader = __ffs((int)m) - 1;
+    if (lane == leader) base = (int)atomicAdd(counter, (u32)__popc(m));
+    base = __shfl_sync(NTL_FULL, base, leader);
+    if (on) items[base + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
 /* =============================================================================================================
@@ -303,8 +365,8 @@ __global__ void __launch_bounds__(256) ntl_filter_kernel(const ntl_read_args a)
 __device__ __noinline__ double k3_div(double a, double b) { return a / b; }
 
 struct WinTab {                 /* the window table of one track (analyze_subtelos :737-764), never materialised */
-    const uint16_t *cum;
-    int n, S, L;
+    const uint16_t *cnt;        /* covered bases per block of SG positions (K2); window k = blocks k Q .. k Q + Q - 1, */
+    int n, nb, Q, S, L;         /* the last window = every remaining block (n windows, nb blocks)                     */
     int thr_reg, thr_last;      /* smallest telomeric count of a regular window / of this read's last window */
     bool any;                   /* at least one telomeric window on this track                                */
     const u32 *bits;            /* class bits of all windows (1 = telomeric) in shared memory, or NULL        */
@@ -320,8 +382,10 @@ __device__ __forceinline__ double wt_density_of_count(const WinTab &w, int k, in
 }
 __device__ __forceinline__ int wt_count(const WinTab &w, int k)
 {
-    const u32 hi = w.cum[k], lo = k > 0 ? (u32)w.cum[k - 1] : 0u;
-    return (int)((hi - lo) & 0xffffu);
+    const int b0 = k * w.Q, b1 = k == w.n - 1 ? w.nb : b0 + w.Q;
+    int c = 0;
+    for (int b = b0; b < b1; b++) c += (int)w.cnt[b];
+    return c;
 }
 /* class == CCCTAA (NanoTel.R:751-758), i.e. !(count / width < min_density): the smallest such count per width was
  * found on the host with the same double division, so the test is an integer compare here. */
@@ -474,15 +538,10 @@ __device__ __noinline__ int covered_in(const ReadView &rv, const WinTab &w, int 
     int total = 0, kf = klo, kl = khi;
     if (lo != wt_start(w, klo)) { total += local_count(rv, t, lo, wt_end(w, klo), lane); kf = klo + 1; }
     if (hi != wt_end(w, khi)) { total += local_count(rv, t, wt_start(w, khi), hi, lane); kl = khi - 1; }
-    /* whole windows kf .. kl: the prefixes telescope.  They are kept mod 2^16, so a difference is exact as long as
-     * its span covers fewer than 65536 bases: one span of `seg` windows per lane */
-    const int seg = 65535 / w.S;
+    /* whole windows kf .. kl: their blocks, 32 at a time */
     int part = 0;
-    for (int k0 = kf + lane * seg; k0 <= kl; k0 += 32 * seg) {
-        const int k1 = k0 + seg - 1 < kl ? k0 + seg - 1 : kl;
-        const u32 hi16 = w.cum[k1], lo16 = k0 > 0 ? (u32)w.cum[k0 - 1] : 0u;
-        part += (int)((hi16 - lo16) & 0xffffu);
-    }
+    const int b0 = kf * w.Q, b1 = kl == w.n - 1 ? w.nb : (kl + 1) * w.Q;
+    for (int b = b0 + lane; b < b1; b += 32) part += (int)w.cnt[b];
     return total + (int)__reduce_add_sync(NTL_FULL, (unsigned)part);
 }
 
@@ -664,7 +723,7 @@ __device__ __forceinline__ bool triage_first_window_hit(u32 lo, u32 hi, int T)
     return any;
 }
 
-/* Eight lanes per read ("team"), four reads per warp: the team walks the window prefixes of the read's LAST track
+/* Eight lanes per read ("team"), four reads per warp: the team walks the block counts of the read's LAST track
  * (see below) 32 16-byte groups at a time (four independent loads per lane, 512 contiguous bytes per team and step),
  * so the longest read costs n_win / 256 dependent steps, and the loads of a team coalesce. */
 __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
@@ -677,77 +736,70 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
     int r = -1;
     if (slot < a.n_reads) {
         r = a.order[slot];
-        const int S = c_prm.S, T = c_prm.n_tracks;
+        const int S = c_prm.S, T = c_prm.n_tracks, Q = c_prm.Q, SG = c_prm.SG;
         const int L = a.len[r];
         const int n_win = ntl_nwin(L, S);
-        const long long wo = a.win_off[r];
-        /* first word of the read (positions 0..31 hold s[1..18]); issued now so that its DRAM latency overlaps
-         * the window loop.  For a 4-bit read word 4 is another plane: read but not used. */
-        const u32 *q0 = a.packed + a.woff[r];
-        const u32 lo0 = __ldg(q0), hi0 = __ldg(q0 + 4);
+        const int nb = (L + SG - 1) / SG;
+        const long long wo = a.cnt_off[r];
+        const int fmt = a.fmt[r];
+        /* first position word of the read (bits 0..17 hold s[1..18]); issued now so that its DRAM latency overlaps
+         * the window loop.  For a 4-bit read these are other planes: read but not used. */
+        const u32 *q0 = fmt ? a.arena4 + (size_t)a.woff[r] * 4 : a.arena2 + (size_t)a.woff[r] * 2;
+        const u32 lo0 = __ldg(q0), hi0 = __ldg(q0 + 1);
         int status = 0;
         bool simple = true;
         if (a.pass != nullptr && a.pass[r] == 0) status = NTL_READ_FILTERED;
         else {
-            simple = a.fmt[r] == 0 && n_win >= 1 && n_win <= NTL_TRIAGE_MAX_WIN;
+            simple = fmt == 0 && n_win >= 1 && n_win <= NTL_TRIAGE_MAX_WIN;
             if (simple)
                 simple = c_prm.right_edge ? ((n_win >= 2 ? S : L) < L - 200) : (1 + (n_win - 1) * S > 200);
             if (simple) {
-                /* any window with  !(count / width < min_density)  on any track?  Every read's window range starts
-                 * on a multiple of 8 entries, so groups of 8 prefixes are 16-byte aligned. */
+                /* any window with  !(count / width < min_density)  on any track?  Every read's block range starts
+                 * on a multiple of 8 entries, so groups of 8 counts are 16-byte aligned. */
                 const int thr_reg = c_prm.thr_reg;
                 const u32 thr16 = (u32)thr_reg << 16;
                 const int thr_last = (int)a.thr[L - (n_win - 1) * S];
                 bool tel = false;
-                const int full = (n_win - 1) >> 3;               /* groups made of width-S windows only */
                 /* The coverage of the tracks is nested (exact hits c <=1-mismatch hits c those + TVR hits), so a
                  * window's covered count can only grow from track to track: some track has a telomeric window iff
                  * the LAST track has one.  Only that plane is walked: half (a third) of the bytes. */
-                const uint16_t *cm = a.cum[T - 1] + wo;
-                const uint4 *cv = reinterpret_cast<const uint4 *>(cm);
-                u32 carry = 0u;                                  /* last word of the previous step */
-                constexpr int NJ = 4;                            /* independent 16-byte loads in flight per lane */
-                for (int g0 = 0; g0 < full; g0 += 8 * NJ) {
-                    uint4 vv[NJ];
+                const uint16_t *cm = a.cnt[T - 1] + wo;
+                int k_done = 0;                                  /* regular windows decided by the vector walk */
+                if (Q == 1) {
+                    const uint4 *cv = reinterpret_cast<const uint4 *>(cm);
+                    const int full = (n_win - 1) >> 3;           /* groups made of width-S windows only */
+                    constexpr int NJ = 4;                        /* independent 16-byte loads in flight per lane */
+                    for (int g0 = 0; g0 < full; g0 += 8 * NJ) {
+                        uint4 vv[NJ];
 #pragma unroll
-                    for (int j = 0; j < NJ; j++) {
-                        const int g = g0 + 8 * j + sub;
-                        vv[j] = g < full ? __ldg(cv + g) : make_uint4(0u, 0u, 0u, 0u);
-                    }
+                        for (int j = 0; j < NJ; j++) {
+                            const int g = g0 + 8 * j + sub;
+                            vv[j] = g < full ? __ldg(cv + g) : make_uint4(0u, 0u, 0u, 0u);
+                        }
 #pragma unroll
-                    for (int j = 0; j < NJ; j++) {
-                        const int g = g0 + 8 * j + sub;
-                        const uint4 v = vv[j];
-                        u32 prev = __shfl_up_sync(tmask, v.w, 1, 8);
-                        if (sub == 0) prev = carry;
-                        carry = __shfl_sync(tmask, v.w, 7, 8);
-                        if (g < full) {
-                            /* counts are differences of 16-bit prefixes mod 2^16: kept in the upper half of a word
-                             * ((x << 16) drops the other prefix, the wrap is the 32-bit wrap), so a window costs one
-                             * subtraction and one unsigned compare */
-                            const u32 x[4] = {v.x, v.y, v.z, v.w};
-                            u32 ph = prev & 0xffff0000u;
+                        for (int j = 0; j < NJ; j++) {
+                            /* two counts per word: the upper one decides  x >= thr << 16, the lower one after a shift */
+                            const u32 x[4] = {vv[j].x, vv[j].y, vv[j].z, vv[j].w};
 #pragma unroll
                             for (int q = 0; q < 4; q++) {
-                                const u32 xl = x[q] << 16, xh = x[q] & 0xffff0000u;
-                                tel |= xl - ph >= thr16;
-                                tel |= xh - xl >= thr16;
-                                ph = xh;
+                                tel |= x[q] >= thr16;
+                                tel |= (x[q] << 16) >= thr16;
                             }
                         }
                     }
+                    k_done = full << 3;
                 }
-                /* the remaining <= 8 windows (the last one has its own width and threshold), one per lane */
-                {
-                    const int k = (full << 3) + sub;
-                    if (k < n_win) {
-                        const u32 cur = cm[k], pv = k > 0 ? (u32)cm[k - 1] : 0u;
-                        tel |= (int)((cur - pv) & 0xffffu) >= (k == n_win - 1 ? thr_last : thr_reg);
-                    }
+                /* the remaining windows, one per lane and step: regular windows are Q blocks, the last one (own width
+                 * and threshold) is every block that is left */
+                for (int k = k_done + sub; k < n_win; k += 8) {
+                    const int b0 = k * Q, b1 = k == n_win - 1 ? nb : b0 + Q;
+                    int c = 0;
+                    for (int b = b0; b < b1; b++) c += (int)cm[b];
+                    tel |= c >= (k == n_win - 1 ? thr_last : thr_reg);
                 }
                 simple = (__ballot_sync(tmask, tel) & tmask) == 0u;
             }
-            if (simple) simple = !triage_first_window_hit(lo0, hi0, T);
+            if (simple) simple = !triage_first_window_hit(lo0 << 1, hi0 << 1, T);
             if (!simple) cand = true;
         }
         if (!cand) {
@@ -814,48 +866,20 @@ __global__ void __launch_bounds__(128, 8) ntl_locate_kernel(const ntl_read_args 
     }
 }
 
-/* any window of this track with  !(count / width < min_density)?  256 prefixes per warp-wide 16-byte load, all
- * loads independent (the window range of a read starts on a multiple of 8 entries and is padded to one) */
+/* any window of this track with  !(count / width < min_density)?  One window per lane, 32 per step; also leaves the
+ * class bits (1 = telomeric window) in bits[] (shared memory, one warp) when it is given */
 __device__ __noinline__ bool warp_any_telomeric(const WinTab &w, int lane, u32 *bits)
 {
-    /* also leaves the class bits (1 = telomeric window) in bits[] (shared memory, one warp) when it is given:
-     * lane l of a step holds windows 8 l' .. 8 l' + 7, four lanes make one 32-bit word */
-    const uint4 *cv = reinterpret_cast<const uint4 *>(w.cum);
-    const int groups = (w.n + 7) >> 3;
-    const u32 thr16 = (u32)w.thr_reg << 16;
     bool tel = false;
-    for (int g0 = 0; g0 < groups; g0 += 32) {
-        const int g = g0 + lane;
-        u32 b8 = 0u;
-        if (g < groups) {
-            /* 16-bit differences in the upper half of a word, as in the triage kernel; every window is first held
-             * against the width-S threshold, then the read's last window (own width) and the padding are redone */
-            const uint4 v = __ldg(cv + g);
-            const u32 x[4] = {v.x, v.y, v.z, v.w};
-            u32 ph = g > 0 ? (u32)w.cum[8 * g - 1] << 16 : 0u;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const u32 xl = x[q] << 16, xh = x[q] & 0xffff0000u;
-                if (xl - ph >= thr16) b8 |= 1u << (2 * q);
-                if (xh - xl >= thr16) b8 |= 2u << (2 * q);
-                ph = xh;
-            }
-            const int kl = w.n - 1 - 8 * g;
-            if (kl < 8) {
-                b8 &= (1u << kl) - 1u;
-                if (wt_telo_count(w, w.n - 1, wt_count(w, w.n - 1))) b8 |= 1u << kl;
-            }
-        }
-        tel |= b8 != 0u;
-        if (bits != nullptr) {
-            u32 wd = b8 << (8 * (lane & 3));
-            wd |= __shfl_xor_sync(NTL_FULL, wd, 1);
-            wd |= __shfl_xor_sync(NTL_FULL, wd, 2);
-            if ((lane & 3) == 0 && g < groups) bits[g >> 2] = wd;
-        }
+    for (int k0 = 0; k0 < w.n; k0 += 32) {
+        const int k = k0 + lane;
+        const bool t = k < w.n && wt_telo_count(w, k, wt_count(w, k));
+        const u32 word = __ballot_sync(NTL_FULL, t);
+        tel |= word != 0u;
+        if (bits != nullptr && lane == 0) bits[k0 >> 5] = word;
     }
     __syncwarp();
-    return __any_sync(NTL_FULL, tel);
+    return tel;
 }
 
 __device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *state, int lane, u32 *sbits, u32 *ccov, int *cwb)
@@ -864,7 +888,7 @@ __device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *stat
     ntl_stage *stg = a.stages ? reinterpret_cast<ntl_stage *>(a.stages) + (size_t)r * 3 : nullptr;
 
     ReadView rv;
-    rv.L = a.len[r]; rv.fmt = a.fmt[r]; rv.base = a.packed + a.woff[r]; rv.n_words = (rv.L >> 5) + 1;
+    rv_init(rv, a, r);
     rv.ccov = ccov; rv.cwb = cwb;
     __syncwarp();                                                   /* the previous item is done with the cache */
     if (lane < 2) cwb[lane] = NTL_NONE;
@@ -884,7 +908,8 @@ __device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *stat
         int max_width = 0;
         for (int t = t_only; t == t_only; t++) {
             WinTab w;
-            w.cum = a.cum[t] + a.win_off[r]; w.n = n_win > 0 ? n_win : 0; w.S = S; w.L = rv.L;
+            w.cnt = a.cnt[t] + a.cnt_off[r]; w.n = n_win > 0 ? n_win : 0; w.S = S; w.L = rv.L;
+            w.Q = c_prm.Q; w.nb = (rv.L + c_prm.SG - 1) / c_prm.SG;
             w.thr_reg = c_prm.thr_reg;
             w.dens = a.dens;
             w.thr_last = w.n > 0 ? (int)a.thr[wt_end(w, w.n - 1) - wt_start(w, w.n - 1) + 1] : 0;
@@ -954,8 +979,46 @@ __device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *stat
                 else if (mw >= 30) status |= NTL_READ_KEEP;
                 res->status = status;
                 res->n_win = n_win > 0 ? n_win : 0;
-                res->win_offset = a.win_off[r];
+                res->win_offset = a.cnt_off[r];
                 for (int t = T; t < 3; t++) res->track[t] = out[t];
+            }
+        }
+    }
+}
+
+/* =============================================================================================================
+ * K2g: generic scan (any pattern set, any subseq_length; patterns in __constant__ memory).  One warp per read, longest
+ * first; coverage words come from warp_cov (31 words per step), every word adds its covered bits to the blocks it
+ * overlaps with 32-bit atomics on the uint16 pairs (the planes are zeroed before the launch).
+ * ============================================================================================================= */
+__global__ void __launch_bounds__(256) ntl_scan_generic_kernel(const ntl_read_args a)
+{
+    const int lane = threadIdx.x & 31;
+    const int T = c_prm.n_tracks, SG = c_prm.SG;
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = (int)atomicAdd(&a.counters[4], 1u);
+        i = __shfl_sync(NTL_FULL, i, 0);
+        if (i >= a.n_reads) break;
+        const int r = a.order[i];
+        if (a.pass != nullptr && a.pass[r] == 0) continue;
+        ReadView rv;
+        rv_init(rv, a, r);
+        const int L = rv.L;
+        for (int t = 0; t < T; t++) {
+            u32 *plane = reinterpret_cast<u32 *>(a.cnt[t] + a.cnt_off[r]);      /* cnt_off is a multiple of 8 entries */
+            for (int wb = -1; ((wb + 1) << 5) <= L; wb += 31) {
+                u32 hs;
+                const u32 cov = warp_cov(rv, t, wb, lane, &hs);
+                if (lane == 0 || cov == 0u) continue;
+                const int p0 = (wb + lane) << 5;                                 /* position of bit 0 */
+                const int pa = p0 < 1 ? 1 : p0, pb = p0 + 31 > L ? L : p0 + 31;
+                for (int blk = (pa - 1) / SG; blk <= (pb - 1) / SG; blk++) {
+                    const int lo = blk * SG + 1 > pa ? blk * SG + 1 : pa, hi = (blk + 1) * SG < pb ? (blk + 1) * SG : pb;
+                    const u32 m = (NTL_FULL >> (31 - (hi - p0))) & (NTL_FULL << (lo - p0));
+                    const u32 c = (u32)__popc(cov & m);
+                    if (c) atomicAdd(plane + (blk >> 1), c << (16 * (blk & 1)));
+                }
             }
         }
     }
@@ -969,23 +1032,29 @@ extern "C" cudaError_t ntl_k_set_params(const ntl_dev_params *p, cudaStream_t st
     return cudaMemcpyToSymbolAsync(c_prm, p, sizeof(ntl_dev_params), 0, cudaMemcpyHostToDevice, st);
 }
 
-extern "C" cudaError_t ntl_k_scan(const ntl_scan_args *a, int four_bit, int grid, cudaStream_t st)
+extern "C" cudaError_t ntl_k_scan_generic(const ntl_read_args *a, int grid, cudaStream_t st)
 {
-    if (a->n_items <= 0) return cudaSuccess;
-    if (four_bit) ntl_scan_kernel<4><<<grid, 256, 0, st>>>(*a);
-    else ntl_scan_kernel<2><<<grid, 256, 0, st>>>(*a);
+    if (a->n_reads <= 0) return cudaSuccess;
+    ntl_scan_generic_kernel<<<grid, 256, 0, st>>>(*a);
     return cudaGetLastError();
 }
 
-extern "C" cudaError_t ntl_k_scan_occupancy(int *blocks_per_sm)
+extern "C" cudaError_t ntl_k_scan_generic_occupancy(int *blocks_per_sm)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ntl_scan_kernel<2>, 256, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ntl_scan_generic_kernel, 256, 0);
 }
 
 extern "C" cudaError_t ntl_k_filter(const ntl_read_args *a, cudaStream_t st)
 {
     if (a->n_reads <= 0) return cudaSuccess;
     ntl_filter_kernel<<<(a->n_reads * 8 + 255) / 256, 256, 0, st>>>(*a);     /* 8 lanes per read */
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t ntl_k_items(const uint8_t *active, int n_items, int32_t *items, uint32_t *counter, cudaStream_t st)
+{
+    if (n_items <= 0) return cudaSuccess;
+    ntl_items_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(active, n_items, items, counter);
     return cudaGetLastError();
 }
 
@@ -1003,18 +1072,18 @@ extern "C" cudaError_t ntl_k_locate(const ntl_read_args *a, int grid, cudaStream
     return cudaGetLastError();
 }
 
-/* Window prefixes of the kept reads only, packed for the device-to-host copy: entry i of `list` = {read, first
- * destination element}; a read's T rows of pw = n_win rounded up to 8 elements follow each other.  One warp per
- * entry, 16-byte moves (source and destination rows start on multiples of 8 elements). */
+/* Block counts of the kept reads only, packed for the device-to-host copy: entry i of `list` = {read, first
+ * destination element}; a read's T rows of ceil8(blocks) elements follow each other.  One warp per entry, 16-byte
+ * moves (source and destination rows start on multiples of 8 elements). */
 __global__ void __launch_bounds__(128) ntl_gather_windows_kernel(const ntl_read_args a, const int64_t *list, int n_list,
                                                                  uint16_t *dst, int T)
 {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n_list) return;
     const int r = (int)list[2 * i];
-    const int groups = (ntl_nwin(a.len[r], c_prm.S) + 7) >> 3;
+    const int groups = ((a.len[r] + c_prm.SG - 1) / c_prm.SG + 7) >> 3;
     for (int t = 0; t < T; t++) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.cum[t] + a.win_off[r]);
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.cnt[t] + a.cnt_off[r]);
         uint4 *out = reinterpret_cast<uint4 *>(dst + list[2 * i + 1]) + (size_t)t * groups;
         for (int g = lane; g < groups; g += 32) out[g] = __ldg(src + g);
     }

@@ -4,8 +4,9 @@
  * Replaces, for the GPU path, what Biostrings does when readDNAStringSet() encodes letters and when
  * reverseComplement() is applied to the chunk (NanoTel.R:2213, 2219-2221): --rc is folded into the packer, so all
  * coordinates the kernels produce are already in the reverse-complemented frame, as in the reference.
- * Layout: see ntl_dev.h.  AVX2 path: 32 letters -> two movemasks (bit 1 and bit 2 of the ASCII code are the 2-bit
- * code of A/C/G/T in either case); scalar path otherwise.
+ * Layout: see ntl_dev.h (position p = bit (p - 1) of the read's stream, one {lo, hi} or {A, C, G, T} record per 32
+ * positions).  AVX2 path: 32 letters -> two movemasks (bit 1 and bit 2 of the ASCII code are the 2-bit code of
+ * A/C/G/T in either case); scalar path otherwise.
  */
 #include "ntl_pack.h"
 #include <string.h>
@@ -97,14 +98,13 @@ static inline bool block_avx2(const char *s, int64_t L, int rc, int64_t b0, uint
 #endif
 
 #if defined(__x86_64__)
-/* 128 letters -> one 32-byte quad {lo[4], hi[4]} per iteration, branch-free inside: four loads (byte-reversed for
- * --rc), ONE validity test (c | 0x20 must equal the letter its low nibble selects: a=0x61 c=0x63 g=0x67 t=0x74),
- * eight movemasks (ASCII bit 1 -> lo plane, bit 2 -> hi plane; complement = ~hi), one 1-bit shift of the two
- * 128-bit planes (the pad bit), one 32-byte store.  Returns the number of full quads written, or -1 if a letter is
- * not A/C/G/T; the carries are the top bits that belong to bit 0 of the next word. */
+/* 128 letters -> four position words {lo, hi} x 4 = 32 bytes per iteration, branch-free inside: four loads (byte-
+ * reversed for --rc), ONE validity test (c | 0x20 must equal the letter its low nibble selects: a=0x61 c=0x63 g=0x67
+ * t=0x74), eight movemasks (ASCII bit 1 -> lo plane, bit 2 -> hi plane; complement = ~hi), one 32-byte store.
+ * Returns the number of 128-letter groups written, or -1 if a letter is not A/C/G/T. */
 template <bool RC>
 __attribute__((target("avx2")))
-static int64_t pack_quads_avx2_t(const char *s, int64_t L, uint32_t *dst, uint32_t *carry_lo, uint32_t *carry_hi)
+static int64_t pack_groups_avx2_t(const char *s, int64_t L, uint32_t *dst)
 {
     const int64_t full = L >> 7;
     const __m256i lut = _mm256_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0,
@@ -112,32 +112,24 @@ static int64_t pack_quads_avx2_t(const char *s, int64_t L, uint32_t *dst, uint32
     const __m256i rev = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0,
                                          15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
     const __m256i m0f = _mm256_set1_epi8(0x0f), c20 = _mm256_set1_epi8(0x20);
-    uint64_t cl = *carry_lo, ch = *carry_hi;
-    /* software prefetch of the input, two lines per quad: the hardware streamer alone feeds one core with ~8 GB/s on
+    /* software prefetch of the input, two lines per group: the hardware streamer alone feeds one core with ~8 GB/s on
      * the B200 hosts, 4 KiB of explicit look-ahead reach 11 GB/s (16 threads: 87 -> 112 GB/s); NTL_PACK_PF overrides */
     static const int pf_dist = getenv("NTL_PACK_PF") ? atoi(getenv("NTL_PACK_PF")) : 4096;
     /* the packed words are written once and read next by the DMA engine: non-temporal stores save the
-     * write-allocate traffic (e2e 26.2 -> 23.4 ms once the input side was no longer the limit); NTL_PACK_NT=0 disables */
+     * write-allocate traffic; NTL_PACK_NT=0 disables */
     static const bool nt_enabled = !(getenv("NTL_PACK_NT") && getenv("NTL_PACK_NT")[0] == '0');
-    const bool nt_store = nt_enabled && ((uintptr_t)dst & 31) == 0;     /* the batch buffers are; a caller's array may not be */
-    static const bool pf_nta = getenv("NTL_PACK_NTA") != nullptr;
+    const bool nt_store = nt_enabled && ((uintptr_t)dst & 31) == 0;     /* span-aligned reads are; a caller's array may not be */
     for (int64_t qq = 0; qq < full; qq++) {
-        /* --rc: output quad q is made of input bytes [L - 128 (q + 1), L - 128 q); the quads are produced last to
+        /* --rc: output group q is made of input bytes [L - 128 (q + 1), L - 128 q); the groups are produced last to
          * first so that the INPUT is read at ascending addresses (the hardware prefetchers of the host follow an
-         * ascending stream better: +7 % at 16 threads, +18 % on one).  The bit that a quad receives from its
-         * predecessor is then not a running carry but simply the letter next to its input block. */
+         * ascending stream better: +7 % at 16 threads, +18 % on one). */
         const int64_t q = RC ? full - 1 - qq : qq;
         __m256i v[4];
-        if (pf_dist > 0) {
-            const char *pb = RC ? s + (L - ((q + 1) << 7)) : s + (q << 7);
-            if (pf_nta) { _mm_prefetch(pb + pf_dist, _MM_HINT_NTA); _mm_prefetch(pb + pf_dist + 64, _MM_HINT_NTA); }
-            else { _mm_prefetch(pb + pf_dist, _MM_HINT_T0); _mm_prefetch(pb + pf_dist + 64, _MM_HINT_T0); }
-        }
+        const char *b = RC ? s + (L - ((q + 1) << 7)) : s + (q << 7);
+        if (pf_dist > 0) { _mm_prefetch(b + pf_dist, _MM_HINT_T0); _mm_prefetch(b + pf_dist + 64, _MM_HINT_T0); }
         if (!RC) {
-            const char *b = s + (q << 7);
             for (int j = 0; j < 4; j++) v[j] = _mm256_loadu_si256((const __m256i *)(b + 32 * j));
         } else {
-            const char *b = s + (L - ((q + 1) << 7));
             for (int j = 0; j < 4; j++) {
                 __m256i x = _mm256_loadu_si256((const __m256i *)(b + 32 * (3 - j)));
                 x = _mm256_shuffle_epi8(x, rev);
@@ -149,36 +141,17 @@ static int64_t pack_quads_avx2_t(const char *s, int64_t L, uint32_t *dst, uint32
             ok = _mm256_and_si256(ok, _mm256_cmpeq_epi8(_mm256_or_si256(v[j], c20),
                                                         _mm256_shuffle_epi8(lut, _mm256_and_si256(v[j], m0f))));
         if (_mm256_movemask_epi8(ok) != -1) return -1;
-        uint64_t l[4], h[4];
+        alignas(32) uint32_t out[8];
         for (int j = 0; j < 4; j++) {
-            l[j] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v[j], 6));
-            h[j] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v[j], 5));
+            out[2 * j] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v[j], 6));        /* ASCII bit 1 -> code bit 0 */
+            const uint32_t h = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v[j], 5));  /* ASCII bit 2 -> code bit 1 */
+            out[2 * j + 1] = RC ? ~h : h;
         }
-        uint64_t la = l[0] | (l[1] << 32), lb = l[2] | (l[3] << 32);
-        uint64_t ha = h[0] | (h[1] << 32), hb = h[2] | (h[3] << 32);
-        if (RC) { ha = ~ha; hb = ~hb; }
-        uint64_t in_l = cl, in_h = ch;
-        if (RC) {
-            if (q == 0) { in_l = *carry_lo; in_h = *carry_hi; }
-            else {
-                const unsigned c = (unsigned char)s[L - (q << 7)];      /* rc position 128 q: top bit of quad q - 1 */
-                in_l = (c >> 1) & 1u; in_h = ((c >> 2) & 1u) ^ 1u;
-            }
-        }
-        uint64_t out[4];
-        out[0] = (la << 1) | in_l; out[1] = (lb << 1) | (la >> 63);
-        out[2] = (ha << 1) | in_h; out[3] = (hb << 1) | (ha >> 63);
-        if (!RC || qq == 0) { cl = lb >> 63; ch = hb >> 63; }           /* --rc: the last quad is made first */
-        if (nt_store) _mm256_stream_si256((__m256i *)(dst + q * 8), _mm256_loadu_si256((const __m256i *)out));
+        if (nt_store) _mm256_stream_si256((__m256i *)(dst + q * 8), _mm256_load_si256((const __m256i *)out));
         else memcpy(dst + q * 8, out, 32);
     }
     if (nt_store) _mm_sfence();
-    *carry_lo = (uint32_t)cl; *carry_hi = (uint32_t)ch;
     return full;
-}
-static int64_t pack_quads_avx2(const char *s, int64_t L, int rc, uint32_t *dst, uint32_t *carry_lo, uint32_t *carry_hi)
-{
-    return rc ? pack_quads_avx2_t<true>(s, L, dst, carry_lo, carry_hi) : pack_quads_avx2_t<false>(s, L, dst, carry_lo, carry_hi);
 }
 #endif
 
@@ -189,22 +162,14 @@ static bool g_have_avx2 =
     false;
 #endif
 
-static inline void put_word(uint32_t *dst, int words_per_quad, int plane, int64_t w, uint32_t val)
-{
-    dst[(w >> 2) * words_per_quad + plane * 4 + (w & 3)] = val;
-}
-
-int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst)
+int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst, int64_t n_words)
 {
     init_tables();
-    const int64_t n_words = (L >> 5) + 1;
-    const int64_t n_quads = (n_words + 3) >> 2;
-    const int64_t n_blocks = (L + 31) >> 5;          /* unshifted 32-letter blocks */
-    uint32_t carry_lo = 0, carry_hi = 0;             /* bit 31 of the previous block -> bit 0 of the next word */
+    const int64_t n_blocks = (L + 31) >> 5;          /* position words that hold letters */
     int64_t k = 0;
 #if defined(__x86_64__)
     if (g_have_avx2) {
-        const int64_t full = pack_quads_avx2(s, L, rc, dst, &carry_lo, &carry_hi);
+        const int64_t full = rc ? pack_groups_avx2_t<true>(s, L, dst) : pack_groups_avx2_t<false>(s, L, dst);
         if (full < 0) return 1;
         k = full << 2;
     }
@@ -220,17 +185,9 @@ int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst)
 #endif
             ok = block_scalar(s, L, rc, b0, n, &lo, &hi);
         if (!ok) return 1;
-        /* position p = b0 + i + 1 lives at bit index p: shift the block up by one bit */
-        put_word(dst, 8, 0, k, (lo << 1) | carry_lo);
-        put_word(dst, 8, 1, k, (hi << 1) | carry_hi);
-        carry_lo = lo >> 31; carry_hi = hi >> 31;
+        dst[2 * k] = lo; dst[2 * k + 1] = hi;        /* position p = b0 + i + 1 is bit i of word k */
     }
-    /* remaining words of the last quad (the word holding only the carried bit, then zero padding) */
-    for (int64_t w = k; w < n_quads * 4; w++) {
-        put_word(dst, 8, 0, w, carry_lo);
-        put_word(dst, 8, 1, w, carry_hi);
-        carry_lo = carry_hi = 0;
-    }
+    if (n_words > n_blocks) memset(dst + 2 * n_blocks, 0, (size_t)(n_words - n_blocks) * 8);   /* the span's padding */
     return 0;
 }
 
@@ -238,10 +195,10 @@ int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst)
 /* Full 32-letter blocks of a read with IUPAC letters -> the four nibble planes, 32 letters per iteration: letter ->
  * Biostrings nibble through two 16-entry byte shuffles ((c | 0x20) - 0x60 is 1..26 for a letter), --rc = byte
  * reversal + a third shuffle that mirrors the nibble (A<->T, C<->G), one movemask per plane.  Returns the number of
- * blocks done and leaves the carried top bits in carry[]; stops early (blocks done so far) at the first block that
- * holds anything but IUPAC letters -- gap characters and errors are left to the scalar loop. */
+ * blocks done; stops early (blocks done so far) at the first block that holds anything but IUPAC letters -- gap
+ * characters and errors are left to the scalar loop. */
 __attribute__((target("avx2")))
-static int64_t pack_blocks_4bit_avx2(const char *s, int64_t L, int rc, uint32_t *dst, uint32_t carry[4])
+static int64_t pack_blocks_4bit_avx2(const char *s, int64_t L, int rc, uint32_t *dst)
 {
     alignas(32) uint8_t t0[32], t1[32], tc[32];
     for (int i = 0; i < 16; i++) {
@@ -272,41 +229,33 @@ static int64_t pack_blocks_4bit_avx2(const char *s, int64_t L, int rc, uint32_t 
         const __m256i bad = _mm256_or_si256(_mm256_cmpeq_epi8(nib, _mm256_set1_epi8(-1)), _mm256_xor_si256(in, _mm256_set1_epi8(-1)));
         if (_mm256_movemask_epi8(bad) != 0) return k;
         if (rc) nib = _mm256_shuffle_epi8(TC, nib);
-        for (int b = 0; b < 4; b++) {
-            const uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(nib, 7 - b));
-            dst[(k >> 2) * 16 + b * 4 + (k & 3)] = (m << 1) | carry[b];
-            carry[b] = m >> 31;
-        }
+        for (int b = 0; b < 4; b++)
+            dst[4 * k + b] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(nib, 7 - b));
     }
     return nb;
 }
 #endif
 
-int ntl_pack_read_4bit(const char *s, int64_t L, int rc, uint32_t *dst)
+int ntl_pack_read_4bit(const char *s, int64_t L, int rc, uint32_t *dst, int64_t n_words)
 {
     init_tables();
-    const int64_t n_words = (L >> 5) + 1;
-    const int64_t n_quads = (n_words + 3) >> 2;
-    int64_t done = 0;                                   /* 32-letter blocks (= words, up to the carried bit) finished */
-    uint32_t carry[4] = {0u, 0u, 0u, 0u};
+    int64_t done = 0;                                   /* 32-letter blocks (= position words) finished */
 #if defined(__x86_64__)
-    if (g_have_avx2) done = pack_blocks_4bit_avx2(s, L, rc, dst, carry);
+    if (g_have_avx2) done = pack_blocks_4bit_avx2(s, L, rc, dst);
 #endif
-    /* the words from `done` on: zero, the carried bits, then the remaining letters one by one */
-    for (int64_t w = done; w < n_quads * 4; w++)
-        for (int b = 0; b < 4; b++) dst[(w >> 2) * 16 + b * 4 + (w & 3)] = w == done ? carry[b] : 0u;
-    for (int64_t p = (done << 5) + 1; p <= L; p++) {
-        unsigned char c = rc ? (unsigned char)s[L - p] : (unsigned char)s[p - 1];
+    /* the words from `done` on: zero, then the remaining letters one by one */
+    if (n_words > done) memset(dst + 4 * done, 0, (size_t)(n_words - done) * 16);
+    for (int64_t p = (done << 5); p < L; p++) {         /* p: 0-based position in the output frame */
+        unsigned char c = rc ? (unsigned char)s[L - 1 - p] : (unsigned char)s[p];
         uint8_t nb = g_nib[c];
         if (nb == 0xFF) return -1;
         if (rc) nb = comp_nib(nb);
-        const int64_t w = p >> 5;
         const uint32_t bit = 1u << (p & 31);
-        uint32_t *q = dst + (w >> 2) * 16 + (w & 3);
+        uint32_t *q = dst + 4 * (p >> 5);
         if (nb & 1) q[0] |= bit;
-        if (nb & 2) q[4] |= bit;
-        if (nb & 4) q[8] |= bit;
-        if (nb & 8) q[12] |= bit;
+        if (nb & 2) q[1] |= bit;
+        if (nb & 4) q[2] |= bit;
+        if (nb & 8) q[3] |= bit;
     }
     return 0;
 }

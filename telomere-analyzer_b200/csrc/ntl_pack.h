@@ -4,13 +4,14 @@
 #include <stdint.h>
 #include <functional>
 
-/* Pack one read (ASCII, L >= 1) into 2-bit quads {lo[4], hi[4]}; dst holds ceil(((L>>5)+1)/4) * 8 words.
+/* Pack one read (ASCII, L >= 1) into 2-bit position words {lo, hi} (8 bytes per 32 positions, position p = bit
+ * (p - 1) & 31 of word (p - 1) >> 5); dst holds n_words >= ceil(L / 32) records, the ones beyond the read are zeroed.
  * rc != 0: write the reverse complement.  Returns 0, or 1 if the read has a letter other than A/C/G/T (any case);
  * the caller then re-packs it with ntl_pack_read_4bit. */
-int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst);
-/* 4-bit quads {A[4], C[4], G[4], T[4]} (Biostrings code bits; gap letters have none); dst holds n_quads * 16 words.
+int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst, int64_t n_words);
+/* 4-bit position words {A, C, G, T} (Biostrings code bits; gap letters have none), 16 bytes per 32 positions.
  * Returns 0, or -1 if a letter is outside the Biostrings DNA alphabet. */
-int ntl_pack_read_4bit(const char *s, int64_t L, int rc, uint32_t *dst);
+int ntl_pack_read_4bit(const char *s, int64_t L, int rc, uint32_t *dst, int64_t n_words);
 /* Biostrings nibble of a pattern letter (IUPAC, either case), -1 if not allowed. */
 int ntl_pattern_nibble(char c);
 /* fn(begin, end) over [0, n) in grains, on n_threads std::threads (the caller's thread included). */

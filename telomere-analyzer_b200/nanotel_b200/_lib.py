@@ -17,7 +17,9 @@ LIB_PATH = os.path.join(_HERE, "libnanotel_b200.so")
 NTL_OK = 0
 NTL_ERR_ARG, NTL_ERR_PATTERN, NTL_ERR_SEQUENCE, NTL_ERR_CUDA, NTL_ERR_NOMEM, NTL_ERR_JIT, NTL_ERR_STATE = range(-1, -8, -1)
 
-OPT_NO_JIT, OPT_REQUIRE_JIT, OPT_DEBUG_STAGES, OPT_DEVICE_PACK = 1, 2, 4, 8
+OPT_NO_JIT, OPT_REQUIRE_JIT, OPT_DEBUG_STAGES = 1, 2, 4
+SCAN_GENERIC, SCAN_PRECOMPILED, SCAN_CACHED, SCAN_NVRTC = 0, 1, 2, 3
+SCAN_PATH_NAMES = {0: "generic", 1: "precompiled", 2: "cached", 3: "nvrtc"}
 READ_KEEP, READ_FILTERED, READ_REF_ERROR, READ_NO_WINDOWS, READ_IUPAC = 1, 2, 4, 8, 16
 
 
@@ -27,7 +29,8 @@ class Params(C.Structure):
         ("n_tvr", C.c_int32), ("tvr_patterns", C.POINTER(C.c_char_p)),
         ("min_density", C.c_double), ("subseq_length", C.c_int32),
         ("rc", C.c_int32), ("use_filter", C.c_int32), ("right_edge", C.c_int32),
-        ("device", C.c_int32), ("options", C.c_uint32), ("host_threads", C.c_int32), ("reserved", C.c_int32),
+        ("device", C.c_int32), ("options", C.c_uint32), ("host_threads", C.c_int32), ("n_devices", C.c_int32),
+        ("device_ids", C.POINTER(C.c_int32)),
     ]
 
 
@@ -55,6 +58,8 @@ assert RESULT_DTYPE.itemsize == 64
 # every symbol include/nanotel_b200.h declares
 EXPORTS = [
     "ntl_version", "ntl_create", "ntl_destroy", "ntl_last_error", "ntl_scan_batch", "ntl_scan_batch_concat",
+    "ntl_scan_batch_pool", "ntl_scan_path", "ntl_scan_path_note", "ntl_device_count", "ntl_get_shards", "ntl_get_geometry",
+    "ntl_jit_precompile_to", "ntl_jit_get_source",
     "ntl_batch_pack", "ntl_batch_upload", "ntl_batch_run", "ntl_batch_enqueue", "ntl_batch_wait", "ntl_batch_download", "ntl_get_timings", "ntl_stream",
     "ntl_get_windows", "ntl_get_window_counts", "ntl_get_stages", "ntl_jit_compile_check", "ntl_pack_read", "ntl_assign_serials", "ntl_count_windows",
     "ntl_reader_open", "ntl_reader_next", "ntl_reader_error", "ntl_reader_close",
@@ -82,6 +87,17 @@ def load() -> C.CDLL:
     L.ntl_last_error.restype = C.c_char_p
     L.ntl_scan_batch.argtypes = [vp, vp, vp, i32, C.POINTER(vp)]
     L.ntl_scan_batch_concat.argtypes = [vp, vp, vp, i32, C.POINTER(vp)]
+    L.ntl_scan_batch_pool.argtypes = [vp, vp, vp, vp, i32, i32, C.POINTER(vp)]
+    L.ntl_scan_path.argtypes = [vp]
+    L.ntl_scan_path_note.argtypes = [vp]
+    L.ntl_scan_path_note.restype = C.c_char_p
+    L.ntl_device_count.argtypes = [vp]
+    L.ntl_get_shards.argtypes = [vp, vp, vp, i32]
+    L.ntl_get_geometry.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.ntl_jit_precompile_to.argtypes = [C.POINTER(Params), C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    L.ntl_jit_precompile_to.restype = C.c_long
+    L.ntl_jit_get_source.argtypes = [C.POINTER(Params), C.c_char_p, C.c_long]
+    L.ntl_jit_get_source.restype = C.c_long
     L.ntl_batch_pack.argtypes = [vp, vp, vp, i32]
     L.ntl_batch_upload.argtypes = [vp]
     L.ntl_batch_run.argtypes = [vp]
@@ -114,8 +130,9 @@ def load() -> C.CDLL:
 
 
 def make_params(patterns, tvr_patterns=None, min_density=0.6, subseq_length=100, rc=False, use_filter=False,
-                right_edge=False, device=0, options=0, host_threads=0) -> Params:
-    """patterns / tvr_patterns: a whitespace separated string (as on NanoTel.R's command line) or a sequence."""
+                right_edge=False, device=0, options=0, host_threads=0, devices=None) -> Params:
+    """patterns / tvr_patterns: a whitespace separated string (as on NanoTel.R's command line) or a sequence.
+    devices: CUDA ordinals to shard every batch over (None: the single `device`)."""
     def toks(x):
         if x is None:
             return []
@@ -139,5 +156,9 @@ def make_params(patterns, tvr_patterns=None, min_density=0.6, subseq_length=100,
     P.device = int(device)
     P.options = int(options)
     P.host_threads = int(host_threads)
-    P._keepalive = (pats, tvr, arr_p, arr_t)
+    ids = [int(d) for d in devices] if devices else []
+    arr_d = (C.c_int32 * max(len(ids), 1))(*ids)
+    P.n_devices = len(ids)
+    P.device_ids = C.cast(arr_d, C.POINTER(C.c_int32))
+    P._keepalive = (pats, tvr, arr_p, arr_t, arr_d)
     return P

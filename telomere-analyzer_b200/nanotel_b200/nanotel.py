@@ -317,22 +317,30 @@ def write_read_outputs(output_dir: str, reads: Sequence[Read], sc: Scanner, res:
 def run_future_worker_chuncks(input_path: str, output_path: Optional[str], format: str = "fastq", nrec: int = 10000,
                               patterns=None, do_rc: bool = False, use_filter: bool = False, right_edge: bool = True,
                               tvr_patterns=None, *, min_density: float = 0.6, subseq_length: int = 100,
-                              device: int = 0, verbose: bool = True):
+                              device: int = 0, devices: Optional[Sequence[int]] = None, verbose: bool = True):
     """NanoTel.R:2171-2268.  The 8 forked search_patterns() futures of the reference are replaced by one
-    ntl_scan_batch() per chunk; Serial numbers and row order follow the reference's 8-way round-robin split
-    (ntl_assign_serials).  Returns {"df_summary": DataFrame, "all_reads_length_vec": int array}."""
+    ntl_scan_batch() per chunk -- sharded over `devices` when several GPUs are given -- ; Serial numbers and row order
+    follow the reference's 8-way round-robin split (ntl_assign_serials).  A read on which NanoTel.R itself would
+    stop() (NTL_READ_REF_ERROR, DESIGN.md "degenerate inputs") stops the run here too.
+    Returns {"df_summary": DataFrame, "all_reads_length_vec": int array}."""
     files = list_input_files(input_path)
     all_len: List[np.ndarray] = []
     rows = []
     serial_start = 1
     with Scanner(_tokens(patterns), _tokens(tvr_patterns) or None, min_density, subseq_length, rc=do_rc,
-                 use_filter=use_filter, right_edge=right_edge, device=device) as sc:
+                 use_filter=use_filter, right_edge=right_edge, device=device, devices=devices) as sc:
+        if sc.note and verbose:
+            print("note:", sc.note, file=sys.stderr)
         for ci, (names, buf, soff) in enumerate(NativeReader(files, format, nrec), 1):
             if verbose:
                 print(time.strftime("%Y-%m-%d %H:%M:%S"))
                 print("processing chunk", ci, "...")
             all_len.append(np.diff(soff))                                               # :2225 (before the filter)
             res = sc.scan_concat(buf, soff)
+            bad = np.flatnonzero(res["status"] & _lib.READ_REF_ERROR)
+            if len(bad):
+                raise RuntimeError("NanoTel.R would have stopped on read(s) %s of chunk %d (%s)" %
+                                   (" ".join(str(int(i) + 1) for i in bad[:10]), ci, names[int(bad[0])]))
             serial, order, serial_start = assign_serials(res, serial_start)             # :2234-2258
             chunk = _LazyChunk(names, buf, soff)
             rows += _rows_from_results(chunk, res, serial, order, sc.n_tracks)
@@ -362,6 +370,9 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--analysis", action="store_true", default=False,
                     help="post-processing of the reference (NanoTel.R:2438-2508) -- not part of the CUDA path")
     ap.add_argument("--device", type=int, default=0, help="CUDA device ordinal (extension)")
+    ap.add_argument("--devices", default=None,
+                    help='space or comma separated CUDA ordinals, or "all": every --nrec chunk is sharded over them '
+                         "(extension; replaces the 8 forked workers of NanoTel.R:2207)")
     return ap
 
 
@@ -378,9 +389,17 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
         sys.exit("Missing required parameter:  --input_path")
     os.makedirs(opt.save_path, exist_ok=True)
     t1 = time.time()
+    devices = None
+    if opt.devices:
+        if opt.devices.strip() == "all":
+            import torch
+            devices = list(range(torch.cuda.device_count()))
+        else:
+            devices = [int(x) for x in opt.devices.replace(",", " ").split()]
     ans = run_future_worker_chuncks(opt.input_path, opt.save_path, opt.format, opt.nrec, opt.patterns, opt.rc,
                                     opt.use_filter, opt.check_right_edge, opt.tvr_patterns,
-                                    min_density=opt.min_density, subseq_length=opt.subseq_length, device=opt.device)
+                                    min_density=opt.min_density, subseq_length=opt.subseq_length, device=opt.device,
+                                    devices=devices)
     df = ans["df_summary"]
     barcode_name = os.path.basename(os.path.normpath(opt.input_path))
     write_summary_csv(df, os.path.join(opt.save_path, barcode_name + "_summary.csv"))        # :2430-2432

@@ -24,7 +24,12 @@ class Scanner:
 
     def __init__(self, patterns, tvr_patterns=None, min_density: float = 0.6, subseq_length: int = 100,
                  rc: bool = False, use_filter: bool = False, right_edge: bool = False, device: int = 0,
-                 jit: Optional[bool] = None, debug_stages: bool = False, host_threads: int = 0):
+                 jit: Optional[bool] = None, debug_stages: bool = False, host_threads: int = 0,
+                 devices: Optional[Sequence[int]] = None):
+        """jit: None = the specialised span scan kernel if one can be had (precompiled, cached or NVRTC), else the
+        generic kernel with a warning; True = fail without it; False = the generic kernel.
+        devices: CUDA ordinals to shard every batch over (contiguous shards balanced by bases, gathered in input
+        order); None = the single `device`."""
         self._L = _lib.load()
         options = 0
         if jit is False:
@@ -34,7 +39,7 @@ class Scanner:
         if debug_stages:
             options |= _lib.OPT_DEBUG_STAGES
         self.params = _lib.make_params(patterns, tvr_patterns, min_density, subseq_length, rc, use_filter,
-                                       right_edge, device, options, host_threads)
+                                       right_edge, device, options, host_threads, devices)
         self.n_tracks = 3 if self.params.n_tvr > 0 else 2
         self.debug_stages = debug_stages
         self._h = C.c_void_p()
@@ -70,7 +75,30 @@ class Scanner:
 
     @property
     def note(self) -> str:
-        return self._L.ntl_last_error(self._h).decode(errors="replace")
+        """Why the context runs the generic scan kernel ("" when it runs the specialised one)."""
+        return self._L.ntl_scan_path_note(self._h).decode(errors="replace")
+
+    @property
+    def scan_path(self) -> str:
+        """"precompiled" | "cached" | "nvrtc" (specialised span scan) or "generic"."""
+        return _lib.SCAN_PATH_NAMES.get(self._L.ntl_scan_path(self._h), "?")
+
+    @property
+    def n_devices(self) -> int:
+        return int(self._L.ntl_device_count(self._h))
+
+    def shards(self):
+        """(bounds[n_devices + 1], devices[n_devices]) of the last batch."""
+        g = self.n_devices
+        b = np.zeros(g + 1, np.int32)
+        d = np.zeros(g, np.int32)
+        self._L.ntl_get_shards(self._h, b.ctypes.data, d.ctypes.data, g)
+        return b, d
+
+    def geometry(self) -> dict:
+        v = [C.c_int32() for _ in range(4)]
+        self._L.ntl_get_geometry(self._h, *[C.byref(x) for x in v])
+        return dict(zip(("block", "blocks_per_window", "words_per_span", "blocks_per_span"), (x.value for x in v)))
 
     # -- batches
     @staticmethod
@@ -128,6 +156,20 @@ class Scanner:
         n = len(offsets) - 1
         res = C.c_void_p()
         self._check(self._L.ntl_scan_batch_concat(self._h, buf.ctypes.data, offsets.ctypes.data, n, C.byref(res)))
+        self._n = n
+        return self._results_view(res, n, out)
+
+    def scan_pool(self, pool: np.ndarray, start: np.ndarray, width: np.ndarray, biostrings_codes: bool = False,
+                  out=None) -> np.ndarray:
+        """ntl_scan_batch_pool: reads as an XStringSet holds them (pool of bytes + 1-based start + width)."""
+        pool = np.ascontiguousarray(pool, dtype=np.uint8)
+        start = np.ascontiguousarray(start, dtype=np.int32)
+        width = np.ascontiguousarray(width, dtype=np.int32)
+        self._keep = (pool, start, width)
+        n = len(start)
+        res = C.c_void_p()
+        self._check(self._L.ntl_scan_batch_pool(self._h, pool.ctypes.data, start.ctypes.data, width.ctypes.data, n,
+                                                int(bool(biostrings_codes)), C.byref(res)))
         self._n = n
         return self._results_view(res, n, out)
 

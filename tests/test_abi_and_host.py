@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported():
     for sym in sorted(declared):
         assert hasattr(L, sym), "libnanotel_b200.so does not export %s" % sym
     assert declared == set(_l.EXPORTS), declared ^ set(_l.EXPORTS)
-    assert L.ntl_version() == 100
+    assert L.ntl_version() == 200
 
 
 def test_struct_layouts():
@@ -46,7 +46,8 @@ def test_no_cpu_fallback_without_a_device():
 
 
 @pytest.mark.parametrize("pats,tvr,S", [("TTAGGG", None, 100), ("YYAGGG", "TTGGG CCAGGG TCAGGG", 100),
-                                         ("CCCTAA CCCTGA", "CCCAA", 500), ("N", None, 7), ("ACGTACGTACGTACGTAC", None, 200)])
+                                         ("CCCTAA CCCTGA", "CCCAA", 500), ("N", None, 16), ("ACGTACGTACGTACGTAC", None, 200),
+                                         ("TTAGGG", None, 20), ("TTAGGG", None, 150), ("TTAGGG", None, 64)])
 def test_nvrtc_specialisation_compiles_for_sm_100a(pats, tvr, S, tmp_path):
     _l, L = _lib()
     P = _l.make_params(pats, tvr, subseq_length=S, rc=True)
@@ -55,6 +56,34 @@ def test_nvrtc_specialisation_compiles_for_sm_100a(pats, tvr, S, tmp_path):
     n = L.ntl_jit_compile_check(C.byref(P), b"sm_100a", log, 1 << 16, cubin)
     assert n > 1000, log.value.decode(errors="replace")
     assert os.path.getsize(cubin) == n
+
+
+@pytest.mark.parametrize("S", [7, 37, 333, 1, 43690])
+def test_subseq_lengths_without_a_span_geometry_are_left_to_the_generic_kernel(S):
+    """No divisor >= 16 of S has an odd part <= 32: there is no specialised build (ntl_create then runs the generic
+    scan kernel and says so through ntl_scan_path / ntl_scan_path_note)."""
+    _l, L = _lib()
+    P = _l.make_params("TTAGGG", None, subseq_length=S)
+    log = C.create_string_buffer(4096)
+    assert L.ntl_jit_compile_check(C.byref(P), b"sm_100a", log, 4096, None) == _l.NTL_ERR_JIT
+    assert b"generic" in log.value
+    P = _l.make_params("TTAGGG", None, subseq_length=43691)
+    assert L.ntl_jit_compile_check(C.byref(P), b"sm_100a", log, 4096, None) == _l.NTL_ERR_ARG
+
+
+def test_precompiled_cubins_ship_next_to_the_library():
+    """build.py specialises the span scan ahead of time for the default pattern sets: files named by their key, with
+    a verified header, in nanotel_b200/precompiled/."""
+    from nanotel_b200 import _lib as _l
+    d = os.path.join(os.path.dirname(_l.LIB_PATH), "precompiled")
+    files = [f for f in os.listdir(d) if f.endswith(".cubin")]
+    assert len(files) >= 8
+    for f in files:
+        raw = open(os.path.join(d, f), "rb").read()
+        assert raw[:8] == b"NTLCUBN2" and len(f) == 32 + 6
+        ka, kb, size = np.frombuffer(raw[8:32], np.uint64)
+        assert f == "%016x%016x.cubin" % (int(ka), int(kb)) and len(raw) == 40 + int(size)
+        assert raw[40:44] == b"\x7fELF"
 
 
 @pytest.mark.parametrize("bad,code", [((["TTAGGG", ""], None), -2), (("TTAGGX", None), -2), (("A" * 19, None), -2),

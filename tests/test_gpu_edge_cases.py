@@ -42,15 +42,19 @@ def test_very_long_reads(S, L):
 
 
 def test_empty_batch_and_tiny_reads():
-    from nanotel_b200 import NanoTelError, Scanner
+    from nanotel_b200 import READ_FILTERED, READ_KEEP, READ_REF_ERROR, NanoTelError, Scanner
+    with Scanner("TTAGGG", use_filter=True) as sc:
+        res = sc.scan([b"", b"ACGT" * 300, b""])                    # width < 1000: filter_reads drops them (:2124)
+        assert all(r["status"] & READ_FILTERED for r in res) and not any(r["status"] & READ_REF_ERROR for r in res)
     with Scanner("TTAGGG") as sc:
         res = sc.scan([])
         assert len(res) == 0
         res = sc.scan([b"A"])
         assert len(res) == 1 and res[0]["n_win"] == 0 and not (res[0]["status"] & 1)
-        with pytest.raises(NanoTelError) as e:
-            sc.scan([b"ACGT", b""])
-        assert e.value.code == -3                                   # zero-length read: NanoTel.R stops (:216)
+        # a zero-length read: NanoTel.R stops on it (seq(1, 0, by = S), :216) unless filter_reads dropped it first
+        res = sc.scan([b"ACGT", b"", b"TTAGGG" * 50])
+        assert res[1]["status"] & READ_REF_ERROR and not (res[1]["status"] & READ_KEEP)
+        assert res[2]["status"] & READ_KEEP and not (res[0]["status"] & (READ_KEEP | READ_REF_ERROR))
         with pytest.raises(NanoTelError) as e:
             sc.scan([b"ACGTJ"])
         assert e.value.code == -3                                   # not a DNA letter

@@ -1,6 +1,6 @@
 """CPU: the host packer (AVX2 + scalar tails, --rc folded in, 4-bit fallback) against a plain numpy restatement of
-the layout in csrc/ntl_dev.h: position p (1-based, after rc) is bit p of the read's stream; quads of 128 positions are
-{lo[4], hi[4]} with code (ASCII >> 1) & 3, or {A[4], C[4], G[4], T[4]} for reads with IUPAC letters."""
+the layout in csrc/ntl_dev.h: position p (1-based, after rc) is bit (p - 1) of the read's stream; every 32 positions
+are one record {lo, hi} with code (ASCII >> 1) & 3, or {A, C, G, T} for reads with IUPAC letters."""
 import ctypes as C
 
 import numpy as np
@@ -29,12 +29,11 @@ def _pack(seq: bytes, rc: bool, misalign: int = 0):
 def _expected(seq: bytes, rc: bool):
     from oracle import oracle as O
     s = O.revcomp(seq) if rc else seq.upper()
-    n_words = (len(s) >> 5) + 1
-    n_quads = (n_words + 3) // 4
+    n_words = (len(s) + 31) >> 5
     acgt = all(c in b"ACGT" for c in s)
     planes = 2 if acgt else 4
-    bits = np.zeros((planes, n_quads * 128), np.uint8)
-    for p, c in enumerate(s, 1):
+    bits = np.zeros((planes, n_words * 32), np.uint8)
+    for p, c in enumerate(s):
         if acgt:
             code = (c >> 1) & 3
             bits[0, p] = code & 1
@@ -43,11 +42,9 @@ def _expected(seq: bytes, rc: bool):
             nb = NIB[c]
             for k in range(4):
                 bits[k, p] = (nb >> k) & 1
-    words = np.zeros(n_quads * 4 * planes, np.uint32)
+    words = np.zeros(n_words * planes, np.uint32)
     for k in range(planes):
-        w = np.packbits(bits[k].reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).ravel()
-        for q in range(n_quads):
-            words[q * 4 * planes + 4 * k: q * 4 * planes + 4 * k + 4] = w[4 * q: 4 * q + 4]
+        words[k::planes] = np.packbits(bits[k].reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).ravel()
     return words, not acgt
 
 
