@@ -768,6 +768,7 @@ int dev_enqueue(ntl_dev_ctx *c)
             sa.flags = ra.span_flags[arena];
             if (filt) { sa.items = item_list + (arena ? items2 : 0); sa.n_items_dev = ra.counters + 2 + arena; }
             sa.n_items = (int32_t)(arena ? items4 : items2);
+            sa.work_counter = ra.counters + 5 + arena;
             sa.n_reads = n; sa.len = ra.len; sa.woff = ra.woff; sa.fmt = ra.fmt; sa.pass = ra.pass;
             sa.cnt_base = arena ? c->spans2 * c->dev.BPS : 0;
             for (int t = 0; t < 3; t++) sa.cnt[t] = ra.cnt[t];

@@ -82,6 +82,7 @@ typedef struct {
     const int32_t  *items;             /* work items (groups of 32 spans) to scan, or NULL = all of them          */
     const uint32_t *n_items_dev;       /* number of entries of items[] (device memory), or NULL                   */
     int32_t         n_items;           /* ceil(n_spans / 32) when items == NULL                                   */
+    uint32_t       *work_counter;      /* zeroed before the launch: hands out the tail units, then the items       */
     int32_t         n_reads;           /* tail pass: reads of the whole batch ...                                 */
     const int32_t  *len;               /* [n_reads]                                                               */
     const int64_t  *woff;              /* [n_reads] first position word of the read inside ITS arena              */
@@ -107,7 +108,8 @@ typedef struct {
     const int32_t  *order;             /* [n_reads] read indices, longest first (triage walks reads in this order)   */
     int32_t        *cand;              /* [n_reads] reads the triage kernel hands on to the locate kernel            */
     int32_t        *cand_state;        /* [n_reads][4] per candidate: tracks done, width of track 0, 1, 2             */
-    uint32_t       *counters;          /* [0] entries in cand[], [1] locate work counter, [2] entries in items[]     */
+    uint32_t       *counters;          /* [0] entries in cand[], [1] locate work counter, [2], [3] entries of the item
+                                          lists of the two arenas, [4] generic scan, [5], [6] span scan work counters  */
     void           *results;           /* ntl_read_result[n_reads]                                                */
     void           *stages;            /* ntl_stage[n_reads][3] or NULL                                           */
     uint8_t        *span_flags[2];     /* per arena: NTL_SPAN_* (the filter rewrites SKIP), or NULL                */

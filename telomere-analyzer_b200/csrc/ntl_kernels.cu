@@ -183,12 +183,49 @@ __device__ __forceinline__ void word_hits(const ntl_dev_pat &pt, const u32 (&pw)
  * get_density_iranges, NanoTel.R:308-397) for read words wbase .. wbase+31, one word per lane: lane l holds positions
  * 32 (wbase + l) .. +31.  Lane 0 lacks the spill of word wbase-1: callers start one word early and ignore lane 0.
  * *hs = exact hit starts of main pattern 0 (the raw hit list of NanoTel.R:349-354). */
+/* planes A, C, G, T (one-hot or IUPAC) of virtual words wbase + lane (pw) and wbase + lane + 1 (pn), zero outside
+ * [1, L]: every lane loads ONE raw record (plus lanes 0 / 31 the record before / after the block) and takes its
+ * neighbours' by shuffle -- virtual word w = raw words (w - 1, w) shifted up by one bit */
+__device__ __forceinline__ void warp_word_planes(const ReadView &rv, int wbase, int lane, u32 (&pw)[4], u32 (&pn)[4])
+{
+    const int w = wbase + lane;
+    const int NP = rv.fmt ? 4 : 2;
+    u32 own[4] = {0u, 0u, 0u, 0u}, ext[4] = {0u, 0u, 0u, 0u};
+    const int xe = lane == 0 ? wbase - 1 : wbase + 32;             /* only lanes 0 and 31 use theirs */
+    if (rv.fmt == 0) {
+        if (w >= 0 && w < rv.n_raw) { const uint2 v = *reinterpret_cast<const uint2 *>(rv.base + (size_t)w * 2); own[0] = v.x; own[1] = v.y; }
+        if ((lane == 0 || lane == 31) && xe >= 0 && xe < rv.n_raw) { const uint2 v = *reinterpret_cast<const uint2 *>(rv.base + (size_t)xe * 2); ext[0] = v.x; ext[1] = v.y; }
+    } else {
+        if (w >= 0 && w < rv.n_raw) { const uint4 v = *reinterpret_cast<const uint4 *>(rv.base + (size_t)w * 4); own[0] = v.x; own[1] = v.y; own[2] = v.z; own[3] = v.w; }
+        if ((lane == 0 || lane == 31) && xe >= 0 && xe < rv.n_raw) { const uint4 v = *reinterpret_cast<const uint4 *>(rv.base + (size_t)xe * 4); ext[0] = v.x; ext[1] = v.y; ext[2] = v.z; ext[3] = v.w; }
+    }
+    u32 vw[4], vn[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (k < NP) {
+            u32 prev = __shfl_up_sync(NTL_FULL, own[k], 1), next = __shfl_down_sync(NTL_FULL, own[k], 1);
+            if (lane == 0) prev = ext[k];
+            if (lane == 31) next = ext[k];
+            vw[k] = __funnelshift_l(prev, own[k], 1);
+            vn[k] = __funnelshift_l(own[k], next, 1);
+        } else { vw[k] = 0u; vn[k] = 0u; }
+    }
+    const u32 mw = (w < 0 || w >= rv.n_words) ? 0u : ntl_valid_word(w << 5, rv.L);
+    const u32 mn = (w + 1 < 0 || w + 1 >= rv.n_words) ? 0u : ntl_valid_word((w + 1) << 5, rv.L);
+    if (rv.fmt == 0) {
+        pw[0] = ~vw[1] & ~vw[0] & mw; pw[1] = ~vw[1] & vw[0] & mw; pw[2] = vw[1] & vw[0] & mw; pw[3] = vw[1] & ~vw[0] & mw;
+        pn[0] = ~vn[1] & ~vn[0] & mn; pn[1] = ~vn[1] & vn[0] & mn; pn[2] = vn[1] & vn[0] & mn; pn[3] = vn[1] & ~vn[0] & mn;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) { pw[k] = vw[k] & mw; pn[k] = vn[k] & mn; }
+    }
+}
+
 __device__ __noinline__ u32 warp_cov(const ReadView &rv, int t, int wbase, int lane, u32 *hs)
 {
     const int w = wbase + lane;
     u32 pw[4], pn[4];
-    word_planes(rv, w, pw);
-    word_planes(rv, w + 1, pn);
+    warp_word_planes(rv, wbase, lane, pw, pn);
     u32 cov = 0u, h0 = 0u;
 #pragma unroll 1
     for (int p = 0; p < c_prm.n_main; p++) {
@@ -382,6 +419,7 @@ __device__ __forceinline__ double wt_density_of_count(const WinTab &w, int k, in
 }
 __device__ __forceinline__ int wt_count(const WinTab &w, int k)
 {
+    if (w.Q == 1 && k < w.n - 1) return (int)w.cnt[k];
     const int b0 = k * w.Q, b1 = k == w.n - 1 ? w.nb : b0 + w.Q;
     int c = 0;
     for (int b = b0; b < b1; b++) c += (int)w.cnt[b];
@@ -866,11 +904,45 @@ __global__ void __launch_bounds__(128, 8) ntl_locate_kernel(const ntl_read_args 
     }
 }
 
-/* any window of this track with  !(count / width < min_density)?  One window per lane, 32 per step; also leaves the
- * class bits (1 = telomeric window) in bits[] (shared memory, one warp) when it is given */
+/* any window of this track with  !(count / width < min_density)?  Also leaves the class bits (1 = telomeric
+ * window) in bits[] (shared memory, one warp) when it is given.  A window that is one block (Q == 1): 256 counts per
+ * warp-wide 16-byte load (a read's block range starts on a multiple of 8 entries), lane l holds windows 8 l .. 8 l + 7,
+ * four lanes make one 32-bit word; else one window per lane. */
 __device__ __noinline__ bool warp_any_telomeric(const WinTab &w, int lane, u32 *bits)
 {
     bool tel = false;
+    if (w.Q == 1) {
+        const uint4 *cv = reinterpret_cast<const uint4 *>(w.cnt);
+        const int groups = (w.n + 7) >> 3;
+        const u32 thr16 = (u32)w.thr_reg << 16;
+        for (int g0 = 0; g0 < groups; g0 += 32) {
+            const int g = g0 + lane;
+            u32 b8 = 0u;
+            if (g < groups) {
+                const uint4 v = __ldg(cv + g);
+                const u32 x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if ((x[q] << 16) >= thr16) b8 |= 1u << (2 * q);
+                    if (x[q] >= thr16) b8 |= 2u << (2 * q);
+                }
+                const int kl = w.n - 1 - 8 * g;            /* the read's last window (own width: it takes every block left) */
+                if (kl < 8) {
+                    b8 &= (1u << kl) - 1u;
+                    if (wt_telo_count(w, w.n - 1, wt_count(w, w.n - 1))) b8 |= 1u << kl;
+                }
+            }
+            tel |= b8 != 0u;
+            if (bits != nullptr) {
+                u32 wd = b8 << (8 * (lane & 3));
+                wd |= __shfl_xor_sync(NTL_FULL, wd, 1);
+                wd |= __shfl_xor_sync(NTL_FULL, wd, 2);
+                if ((lane & 3) == 0 && g < groups) bits[g >> 2] = wd;
+            }
+        }
+        __syncwarp();
+        return __any_sync(NTL_FULL, tel);
+    }
     for (int k0 = 0; k0 < w.n; k0 += 32) {
         const int k = k0 + lane;
         const bool t = k < w.n && wt_telo_count(w, k, wt_count(w, k));

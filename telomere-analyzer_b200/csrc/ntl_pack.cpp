@@ -104,9 +104,14 @@ static inline bool block_avx2(const char *s, int64_t L, int rc, int64_t b0, uint
  * Returns the number of 128-letter groups written, or -1 if a letter is not A/C/G/T. */
 template <bool RC>
 __attribute__((target("avx2")))
-static int64_t pack_groups_avx2_t(const char *s, int64_t L, uint32_t *dst)
+static int64_t pack_groups_avx2_t(const char *s, int64_t L, uint32_t *dst, int64_t w0)
 {
-    const int64_t full = L >> 7;
+    /* the groups cover position words w0, w0 + 4, ... (w0 < 4 head words are left to the caller so that every
+     * 32-byte store of a group is aligned: a read starts at a multiple of 8 bytes, not of 32) */
+    const int64_t full = (L - 32 * w0) >> 7;
+    if (full <= 0) return 0;
+    dst += 2 * w0;
+    if (RC) L -= 32 * w0; else s += 32 * w0;     /* output word w0 = letters [32 w0, ..) forward, [.., L - 32 w0) reversed */
     const __m256i lut = _mm256_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0,
                                          0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0);
     const __m256i rev = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0,
@@ -118,7 +123,7 @@ static int64_t pack_groups_avx2_t(const char *s, int64_t L, uint32_t *dst)
     /* the packed words are written once and read next by the DMA engine: non-temporal stores save the
      * write-allocate traffic; NTL_PACK_NT=0 disables */
     static const bool nt_enabled = !(getenv("NTL_PACK_NT") && getenv("NTL_PACK_NT")[0] == '0');
-    const bool nt_store = nt_enabled && ((uintptr_t)dst & 31) == 0;     /* span-aligned reads are; a caller's array may not be */
+    const bool nt_store = nt_enabled && ((uintptr_t)dst & 31) == 0;
     for (int64_t qq = 0; qq < full; qq++) {
         /* --rc: output group q is made of input bytes [L - 128 (q + 1), L - 128 q); the groups are produced last to
          * first so that the INPUT is read at ascending addresses (the hardware prefetchers of the host follow an
@@ -166,15 +171,17 @@ int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst, int64_t 
 {
     init_tables();
     const int64_t n_blocks = (L + 31) >> 5;          /* position words that hold letters */
-    int64_t k = 0;
+    int64_t k = 0, k_skip_lo = 0, k_skip_hi = 0;     /* words [k_skip_lo, k_skip_hi) were written by the vector loop */
 #if defined(__x86_64__)
     if (g_have_avx2) {
-        const int64_t full = rc ? pack_groups_avx2_t<true>(s, L, dst) : pack_groups_avx2_t<false>(s, L, dst);
+        const int64_t w0 = ((uintptr_t)dst & 7) == 0 ? (int64_t)(((32 - ((uintptr_t)dst & 31)) & 31) >> 3) : 0;
+        const int64_t full = rc ? pack_groups_avx2_t<true>(s, L, dst, w0) : pack_groups_avx2_t<false>(s, L, dst, w0);
         if (full < 0) return 1;
-        k = full << 2;
+        if (full > 0) { k_skip_lo = w0; k_skip_hi = w0 + (full << 2); }
     }
 #endif
     for (; k < n_blocks; k++) {
+        if (k == k_skip_lo && k_skip_hi > k_skip_lo) { k = k_skip_hi - 1; continue; }
         uint32_t lo, hi;
         const int64_t b0 = k << 5;
         const int n = L - b0 >= 32 ? 32 : (int)(L - b0);
