@@ -1073,11 +1073,8 @@ extern "C" int ntl_create(ntl_ctx **out, const ntl_params *p)
     std::vector<int32_t> ids;
     if (p->n_devices > 0) {
         if (!p->device_ids || p->n_devices > NTL_MAX_DEVICES) return fail(nullptr, NTL_ERR_ARG, "n_devices must be 0..%d with device_ids", NTL_MAX_DEVICES);
-        for (int i = 0; i < p->n_devices; i++) {
-            for (int j = 0; j < i; j++)
-                if (p->device_ids[j] == p->device_ids[i]) return fail(nullptr, NTL_ERR_ARG, "device %d is listed twice", p->device_ids[i]);
-            ids.push_back(p->device_ids[i]);
-        }
+        /* a device may be listed more than once: every entry is a shard with its own stream and buffers */
+        for (int i = 0; i < p->n_devices; i++) ids.push_back(p->device_ids[i]);
     } else ids.push_back(p->device);
 
     int nt = p->host_threads;
