@@ -294,6 +294,12 @@ def main():
         except Exception:
             pass
 
+    # stdout carries exactly one JSON line: everything else that libraries print there (NCCL's version banner, ...)
+    # goes to stderr -- file descriptor 1 is pointed at stderr until the line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -477,7 +483,8 @@ def main():
             v, sb, sn, dt = cpu_baseline(buf, offsets, wl, args.cpu_sample, cores)
             line["cpu_baseline"] = {"value": v, "unit": "Gbases/s", "cores": cores, "kind": "port",
                                     "sample": "first %d reads (%d bases) of rank 0's batch, %.1f s" % (sn, sb, dt)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -94,52 +94,6 @@ __device__ __forceinline__ u32 rv_word(const ReadView &rv, int plane, int w)
     return __funnelshift_l(rv_raw(rv, plane, w - 1), rv_raw(rv, plane, w), 1);
 }
 
-/* One-hot (ACGT reads) or IUPAC (4-bit reads) planes A, C, G, T for the 32 positions p .. p+31, zeroed outside
- * [vlo, vhi].  A zero nibble matches nothing under both comparison rules, i.e. counts as a mismatch -- Biostrings'
- * treatment of out-of-bounds letters (App. B.3). */
-__device__ __forceinline__ void rv_fetch4(const ReadView &rv, int p, int vlo, int vhi, u32 (&pl)[4])
-{
-    const int w = p >> 5, s = p & 31;
-    int lowb = vlo - p; if (lowb < 0) lowb = 0;
-    int highb = vhi - p; if (highb > 31) highb = 31;
-    u32 vm = 0u;
-    if (highb >= lowb) vm = (NTL_FULL >> (31 - highb)) & (NTL_FULL << lowb);
-    if (rv.fmt == 0) {
-        const u32 lo = __funnelshift_r(rv_word(rv, 0, w), rv_word(rv, 0, w + 1), s);
-        const u32 hi = __funnelshift_r(rv_word(rv, 1, w), rv_word(rv, 1, w + 1), s);
-        pl[0] = ~hi & ~lo & vm;     /* A = 0 */
-        pl[1] = ~hi & lo & vm;      /* C = 1 */
-        pl[2] = hi & lo & vm;       /* G = 3 */
-        pl[3] = hi & ~lo & vm;      /* T = 2 */
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            pl[k] = __funnelshift_r(rv_word(rv, k, w), rv_word(rv, k, w + 1), s) & vm;
-    }
-}
-
-/* mismatches of the alignment whose first letter sits on bit 0 of pl[] */
-__device__ __forceinline__ int pat_mismatches(const ntl_dev_pat &pt, bool fixed, const u32 (&pl)[4])
-{
-    const u32 mm = (1u << pt.m) - 1u;
-    u32 eq;
-    if (fixed) eq = ~((pl[0] ^ pt.q4[0]) | (pl[1] ^ pt.q4[1]) | (pl[2] ^ pt.q4[2]) | (pl[3] ^ pt.q4[3]));
-    else eq = (pl[0] & pt.q4[0]) | (pl[1] & pt.q4[1]) | (pl[2] & pt.q4[2]) | (pl[3] & pt.q4[3]);
-    return __popc(~eq & mm);
-}
-
-/* Hit-start bits for alignment starts p0 .. p0+31 of one pattern, one alignment per lane
- * (Biostrings::matchPattern, App. B.2/B.3): positions outside [vlo, vhi] are mismatches.
- * mode_fixed < 0: use the pattern's own fixed flag. */
-__device__ __forceinline__ u32 hits32(const ReadView &rv, const ntl_dev_pat &pt, int k, int mode_fixed, int p0, int vlo,
-                                   int vhi, int lane)
-{
-    u32 pl[4];
-    rv_fetch4(rv, p0 + lane, vlo, vhi, pl);
-    const bool fx = mode_fixed < 0 ? (pt.fixed != 0) : (mode_fixed != 0);
-    return __ballot_sync(NTL_FULL, pat_mismatches(pt, fx, pl) <= k);
-}
-
 /* ---- one word per lane: planes of read word w as A/C/G/T bit masks, zero outside [1, L] */
 __device__ __forceinline__ void word_planes(const ReadView &rv, int w, u32 (&pl)[4])
 {
@@ -655,10 +609,34 @@ __device__ __noinline__ int get_accurate_start(const ReadView &rv, int t, int te
 
 /* One 18-bp window of search_left/right_patterns (multi_pattern_step_*, NanoTel.R:496-575, :614, :676):
  * matchPattern on subseq(read, a, b) with the default fixed = TRUE, the window's own out-of-bounds rule, hits not
- * trimmed.  Returns false if no pattern hits. */
-__device__ __noinline__ bool step_window(const ReadView &rv, int a, int b, int k, bool use_tvr, int *min_start,
-                                         int *max_end, int lane)
+ * trimmed.  Returns false if no pattern hits.
+ * The window and every alignment that can hit it (starts a - k .. b - m + 1 + k) fit one 32-bit word whose bit i is
+ * position a - 1 + i: the word is cut out of two position words (the same for all lanes), letters outside [a, b] carry
+ * zero masks (mismatches), and all alignment starts of a pattern are decided together by a two-plane mismatch counter
+ * (Shift-And).  No shuffles: every lane computes the same value. */
+__device__ __noinline__ bool step_window(const ReadView &rv, int a, int b, int k, bool use_tvr, int *min_start, int *max_end)
 {
+    *min_start = 0; *max_end = 0;
+    if (b < a) return false;
+    const int q0 = a - 1;                               /* position of bit 0 */
+    const int rb = q0 - 1;                              /* its index in the packed stream (position p = bit p - 1) */
+    u32 pl[4];
+    {
+        const int x = rb >> 5, sh = rb & 31;            /* rb = -1 (a = 1): x = -1, sh = 31 -> the stream shifted up by one */
+        const int NP = rv.fmt ? 4 : 2;
+        u32 w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+            if (p < NP) w[p] = __funnelshift_r(rv_raw(rv, p, x), rv_raw(rv, p, x + 1), sh);
+        const u32 vm = ((2u << (b - a)) - 1u) << 1;     /* bits 1 .. b - a + 1: the window itself */
+        if (rv.fmt == 0) {
+            pl[0] = ~w[1] & ~w[0] & vm; pl[1] = ~w[1] & w[0] & vm; pl[2] = w[1] & w[0] & vm; pl[3] = w[1] & ~w[0] & vm;
+        } else {
+#pragma unroll
+            for (int p = 0; p < 4; p++) pl[p] = w[p] & vm;
+        }
+    }
+    const u32 vmask = ((2u << (b - a)) - 1u) << 1;
     bool any = false;
     int mn = 0, mx = 0;
     for (int pass = 0; pass < 2; pass++) {
@@ -666,15 +644,24 @@ __device__ __noinline__ bool step_window(const ReadView &rv, int a, int b, int k
         const int kk = pass == 0 ? k : 0;
         for (int p = 0; p < np; p++) {
             const ntl_dev_pat &pt = pass == 0 ? c_prm.main_pat[p] : c_prm.tvr_pat[p];
-            /* alignment starts a - kk .. b - m + 1 + kk : at most 18 - m + 1 + 2 of them */
-            const int s0 = a - kk;
-            u32 h = hits32(rv, pt, kk, 1, s0, a, b, lane);
-            const int nstarts = (b - pt.m + 1 + kk) - s0 + 1;
-            if (nstarts <= 0) continue;
-            if (nstarts < 32) h &= (1u << nstarts) - 1u;
+            const int m = pt.m;
+            /* alignment starts a - kk .. b - m + 1 + kk  <->  bits 1 - kk .. b - a + 2 - m + kk */
+            const int hi_bit = b - a + 2 - m + kk;
+            if (hi_bit < 1 - kk) continue;
+            u32 ones = 0u, twos = 0u;
+            for (int j = 0; j < m; j++) {
+                /* fixed = TRUE: the read's code must EQUAL the pattern letter's code */
+                const u32 mA = pt.mux4[j][0], mC = pt.mux4[j][1], mG = pt.mux4[j][2], mT = pt.mux4[j][3];
+                const u32 e = ~((pl[0] ^ mA) | (pl[1] ^ mC) | (pl[2] ^ mG) | (pl[3] ^ mT)) & vmask;
+                const u32 x = ~(e >> j);
+                twos |= ones & x;
+                ones ^= x;
+            }
+            const u32 sm = ((2u << hi_bit) - 1u) & ~((1u << (1 - kk)) - 1u);
+            const u32 h = (kk ? ~twos : ~(ones | twos)) & sm;
             if (h) {
-                const int lo = s0 + __ffs((int)h) - 1;
-                const int hi = s0 + 31 - __clz((int)h) + pt.m - 1;
+                const int lo = q0 + __ffs((int)h) - 1;
+                const int hi = q0 + 31 - __clz((int)h) + m - 1;
                 if (!any || lo < mn) mn = lo;
                 if (!any || hi > mx) mx = hi;
                 any = true;
@@ -693,7 +680,7 @@ __device__ __noinline__ int search_left(const ReadView &rv, int start_index, int
     for (int i = 0; i < 4; i++) {
         const int curr_end = subseq_start + 17 < rv.L ? subseq_start + 17 : rv.L;
         int mn, mx;
-        if (!step_window(rv, subseq_start, curr_end, k, use_tvr, &mn, &mx, lane)) break;
+        if (!step_window(rv, subseq_start, curr_end, k, use_tvr, &mn, &mx)) break;
         new_start = mn;
         const int nn = subseq_start - 9 > 1 ? subseq_start - 9 : 1;
         if (nn == subseq_start) break;
@@ -710,7 +697,7 @@ __device__ __noinline__ int search_right(const ReadView &rv, int end_index, int 
     for (int i = 0; i < 4; i++) {
         const int curr_start = subseq_end - 17 > 1 ? subseq_end - 17 : 1;
         int mn, mx;
-        if (!step_window(rv, curr_start, subseq_end, k, use_tvr, &mn, &mx, lane)) break;
+        if (!step_window(rv, curr_start, subseq_end, k, use_tvr, &mn, &mx)) break;
         new_end = mx;
         const int nn = subseq_end + 11 < rv.L ? subseq_end + 11 : rv.L;
         if (nn == subseq_end) break;
