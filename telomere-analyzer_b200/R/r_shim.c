@@ -34,11 +34,17 @@ static ntl_ctx *get_ctx(SEXP ptr)
 }
 
 /* ntl_R_create(patterns chr, tvr_patterns chr or NULL, min_density dbl, subseq_length int, rc lgl, use_filter lgl,
- *              right_edge lgl, device int) -> external pointer
- * patterns / tvr_patterns: the character vectors cur_patterns / cur_tvr_patterns of NanoTel.R:2322-2334 (unlist()ed). */
+ *              right_edge lgl, devices int vector) -> external pointer
+ * patterns / tvr_patterns: the character vectors cur_patterns / cur_tvr_patterns of NanoTel.R:2322-2334 (unlist()ed).
+ * devices: CUDA ordinals; with more than one, every chunk is sharded over them (contiguous shards balanced by bases,
+ * records gathered in input order) -- the replacement for plan(multicore, workers = 8) (NanoTel.R:2207). */
 SEXP ntl_R_create(SEXP patterns, SEXP tvr, SEXP min_density, SEXP subseq_length, SEXP rc, SEXP use_filter,
-                  SEXP right_edge, SEXP device)
+                  SEXP right_edge, SEXP devices)
 {
+    int32_t ids[NTL_MAX_DEVICES];
+    const int nd = LENGTH(devices);
+    if (nd < 1 || nd > NTL_MAX_DEVICES) Rf_error("nanotel_b200: 1..%d devices", NTL_MAX_DEVICES);
+    for (int i = 0; i < nd; i++) ids[i] = INTEGER(devices)[i];
     const char *pp[NTL_MAX_PATTERNS], *tp[NTL_MAX_PATTERNS];
     int np = LENGTH(patterns), nt = Rf_isNull(tvr) ? 0 : LENGTH(tvr);
     if (np < 1 || np > NTL_MAX_PATTERNS || nt > NTL_MAX_PATTERNS) Rf_error("nanotel_b200: 1..%d patterns", NTL_MAX_PATTERNS);
@@ -53,10 +59,13 @@ SEXP ntl_R_create(SEXP patterns, SEXP tvr, SEXP min_density, SEXP subseq_length,
     p.rc = Rf_asLogical(rc) == TRUE;
     p.use_filter = Rf_asLogical(use_filter) == TRUE;
     p.right_edge = Rf_asLogical(right_edge) == TRUE;
-    p.device = Rf_asInteger(device);
+    p.device = ids[0];
+    p.n_devices = nd; p.device_ids = ids;
     ntl_ctx *c = NULL;
     int st = ntl_create(&c, &p);
     if (st != NTL_OK) Rf_error("nanotel_b200: ntl_create failed (%d): %s", st, ntl_last_error(NULL));
+    if (ntl_scan_path(c) == NTL_SCAN_GENERIC)           /* never a silent slow path */
+        Rf_warning("nanotel_b200: %s", ntl_scan_path_note(c));
     SEXP ptr = PROTECT(R_MakeExternalPtr(c, R_NilValue, R_NilValue));
     R_RegisterCFinalizerEx(ptr, ctx_finalizer, TRUE);
     UNPROTECT(1);
@@ -67,6 +76,8 @@ SEXP ntl_R_create(SEXP patterns, SEXP tvr, SEXP min_density, SEXP subseq_length,
  * library applies --rc itself).  Returns a named list of vectors of length(seqs):
  *   keep lgl, filtered lgl, ref_error lgl, n_win int,
  *   start / end (int, NA where the reference prints NA) and density (dbl) for tracks "", "_mismatch", "_mismatch_tvr". */
+static SEXP results_to_list(const ntl_read_result *res, int n);
+
 SEXP ntl_R_scan_batch(SEXP ctxp, SEXP seqs)
 {
     ntl_ctx *c = get_ctx(ctxp);
@@ -77,6 +88,36 @@ SEXP ntl_R_scan_batch(SEXP ctxp, SEXP seqs)
     const ntl_read_result *res = NULL;
     int st = ntl_scan_batch(c, sp, len, n, &res);
     if (st != NTL_OK) Rf_error("nanotel_b200: ntl_scan_batch failed (%d): %s", st, ntl_last_error(c));
+    return results_to_list(res, n);
+}
+
+/* ntl_R_scan_xstringset(ctx, dna_reads): the DNAStringSet of NanoTel.R:2213 handed over WITHOUT as.character(): an
+ * XStringSet is a pool of shared raw vectors (x@pool@xp_list[[g]], an external pointer whose tag is the RAWSXP) plus
+ * x@ranges@group / @start / @width; the bytes are Biostrings' DNA codes, which the library decodes itself
+ * (ntl_scan_batch_pool).  Returns NULL if the reads do not all live in one pool element (the caller then falls back
+ * to ntl_R_scan_batch(as.character(dna_reads))); readDNAStringSet() always yields a single one. */
+SEXP ntl_R_scan_xstringset(SEXP ctxp, SEXP x)
+{
+    ntl_ctx *c = get_ctx(ctxp);
+    SEXP ranges = R_do_slot(x, Rf_install("ranges"));
+    SEXP group = R_do_slot(ranges, Rf_install("group"));
+    SEXP start = R_do_slot(ranges, Rf_install("start"));
+    SEXP width = R_do_slot(ranges, Rf_install("width"));
+    const int n = LENGTH(start);
+    if (n == 0) return results_to_list(NULL, 0);
+    const int g0 = INTEGER(group)[0];
+    for (int i = 1; i < n; i++) if (INTEGER(group)[i] != g0) return R_NilValue;
+    SEXP xp_list = R_do_slot(R_do_slot(x, Rf_install("pool")), Rf_install("xp_list"));
+    SEXP raw = R_ExternalPtrTag(VECTOR_ELT(xp_list, g0 - 1));
+    if (TYPEOF(raw) != RAWSXP) return R_NilValue;
+    const ntl_read_result *res = NULL;
+    int st = ntl_scan_batch_pool(c, RAW(raw), INTEGER(start), INTEGER(width), n, /*biostrings_codes=*/1, &res);
+    if (st != NTL_OK) Rf_error("nanotel_b200: ntl_scan_batch_pool failed (%d): %s", st, ntl_last_error(c));
+    return results_to_list(res, n);
+}
+
+static SEXP results_to_list(const ntl_read_result *res, int n)
+{
 
     static const char *names[] = {"keep", "filtered", "ref_error", "n_win",
                                   "start", "end", "density",
@@ -109,22 +150,30 @@ SEXP ntl_R_scan_batch(SEXP ctxp, SEXP seqs)
     return out;
 }
 
-/* ntl_R_windows(ctx, read_index (1-based), track (1..3)) -> data.frame-ready list(ID, start_index, end_index, density):
- * the `subs` table analyze_subtelos returns (NanoTel.R:740-765), consumed unchanged by plot_single_telo_with_*(). */
-SEXP ntl_R_windows(SEXP ctxp, SEXP read_index, SEXP track)
+/* ntl_R_windows(ctx, read_index (1-based), track (1..3), min_density) -> data.frame-ready list(ID, start_index,
+ * end_index, density, class): the `subs` table analyze_subtelos returns (NanoTel.R:740-765; class = -5 CCCTAA /
+ * 1 NONE / 0 SKIP by :749-758), consumed unchanged by plot_single_telo_with_*(). */
+SEXP ntl_R_windows(SEXP ctxp, SEXP read_index, SEXP track, SEXP min_density)
 {
     ntl_ctx *c = get_ctx(ctxp);
     const int i = Rf_asInteger(read_index) - 1, t = Rf_asInteger(track) - 1;
+    const double md = Rf_asReal(min_density);
     int n = ntl_get_windows(c, i, t, 0, NULL, NULL, NULL, NULL);
     if (n < 0) Rf_error("nanotel_b200: ntl_get_windows failed (%d): %s", n, ntl_last_error(c));
-    static const char *names[] = {"ID", "start_index", "end_index", "density", ""};
+    static const char *names[] = {"ID", "start_index", "end_index", "density", "class", ""};
     SEXP out = PROTECT(Rf_mkNamed(VECSXP, names));
     SEXP id = PROTECT(Rf_allocVector(INTSXP, n)), st = PROTECT(Rf_allocVector(INTSXP, n));
     SEXP en = PROTECT(Rf_allocVector(INTSXP, n)), de = PROTECT(Rf_allocVector(REALSXP, n));
+    SEXP cl = PROTECT(Rf_allocVector(REALSXP, n));
     ntl_get_windows(c, i, t, n, INTEGER(st), INTEGER(en), NULL, REAL(de));
-    for (int k = 0; k < n; k++) INTEGER(id)[k] = k + 1;
+    for (int k = 0; k < n; k++) {
+        INTEGER(id)[k] = k + 1;
+        const double d = REAL(de)[k];
+        REAL(cl)[k] = d < md ? (d < 0.1 ? 0.0 : 1.0) : -5.0;      /* :749-758 */
+    }
     SET_VECTOR_ELT(out, 0, id); SET_VECTOR_ELT(out, 1, st); SET_VECTOR_ELT(out, 2, en); SET_VECTOR_ELT(out, 3, de);
-    UNPROTECT(5);
+    SET_VECTOR_ELT(out, 4, cl);
+    UNPROTECT(6);
     return out;
 }
 
@@ -156,7 +205,8 @@ SEXP ntl_R_destroy(SEXP ctxp) { ctx_finalizer(ctxp); return R_NilValue; }
 static const R_CallMethodDef call_methods[] = {
     {"ntl_R_create", (DL_FUNC)&ntl_R_create, 8},
     {"ntl_R_scan_batch", (DL_FUNC)&ntl_R_scan_batch, 2},
-    {"ntl_R_windows", (DL_FUNC)&ntl_R_windows, 3},
+    {"ntl_R_scan_xstringset", (DL_FUNC)&ntl_R_scan_xstringset, 2},
+    {"ntl_R_windows", (DL_FUNC)&ntl_R_windows, 4},
     {"ntl_R_assign_serials", (DL_FUNC)&ntl_R_assign_serials, 3},
     {"ntl_R_destroy", (DL_FUNC)&ntl_R_destroy, 1},
     {NULL, NULL, 0}};

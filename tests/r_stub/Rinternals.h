@@ -12,6 +12,8 @@ typedef enum { FALSE = 0, TRUE } Rboolean;
 #define REALSXP 14
 #define STRSXP 16
 #define VECSXP 19
+#define RAWSXP 24
+typedef unsigned char Rbyte;
 extern SEXP R_NilValue;
 extern int R_NaInt;
 extern double R_NaReal;
@@ -29,6 +31,13 @@ int Rf_asLogical(SEXP);
 double Rf_asReal(SEXP);
 Rboolean Rf_isNull(SEXP);
 void Rf_error(const char *, ...) __attribute__((noreturn));
+void Rf_warning(const char *, ...);
+SEXP Rf_install(const char *);
+SEXP R_do_slot(SEXP, SEXP);
+SEXP VECTOR_ELT(SEXP, R_xlen_t);
+SEXP R_ExternalPtrTag(SEXP);
+int TYPEOF(SEXP);
+Rbyte *RAW(SEXP);
 int LENGTH(SEXP);
 int *INTEGER(SEXP);
 int *LOGICAL(SEXP);

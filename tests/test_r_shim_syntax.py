@@ -27,3 +27,26 @@ def test_r_glue_registers_what_the_r_script_calls():
     registered = set(re.findall(r'\{"(ntl_R_\w+)"', src))
     called = set(re.findall(r'\.Call\("?(ntl_R_\w+)"?', rsrc))
     assert registered and called and called <= registered, (registered, called)
+
+
+def test_r_scripts_draw_the_reference_plots_from_what_the_library_returns():
+    """NanoTelGPU.R calls the reference's own plot functions with the window tables of the library (not a comment),
+    and plot_density_vectors.R reads exactly the columns the R-free driver writes to density_vectors/read<Serial>.csv."""
+    import re
+    rdir = os.path.join(ROOT, "telomere-analyzer_b200", "R")
+    gpu = open(os.path.join(rdir, "NanoTelGPU.R")).read()
+    code = "\n".join(l.split("#")[0] for l in gpu.splitlines())
+    for fn in ("plot_single_telo_with_gray_area", "plot_single_telo_with_tvr", "writeXStringSet", "ntl_R_scan_xstringset"):
+        assert fn in code, fn
+    assert code.count("do.call(plot_single_telo_with_gray_area") == 3 and code.count("do.call(plot_single_telo_with_tvr") == 3
+    plot = open(os.path.join(rdir, "plot_density_vectors.R")).read()
+    py = open(os.path.join(ROOT, "telomere-analyzer_b200", "nanotel_b200", "nanotel.py")).read()
+    assert '"density_vectors"' in py and "density_vectors" in plot
+    for col in ("ID", "start_index", "end_index", "density", "class"):
+        assert '"%s"' % col in py or col in py
+        assert col in plot
+    for sfx in ("_mismatch", "_mismatch_tvr"):
+        assert '"%s"' % sfx in py and '"%s"' % sfx in plot
+    # the summary columns the script reads are the ones write_summary_csv emits
+    for col in re.findall(r"row\$(\w+)", plot):
+        assert col in py or col in ("Serial",), col
