@@ -1,33 +1,67 @@
-"""Wall clock of the R-free command line on synthetic gzip FASTQ files (cfg2-like reads):  cli_bench.py [n_reads] [n_files]"""
+"""File-to-summary wall clock of the R-free command line (python -m nanotel_b200) on synthetic gzip FASTQ files, the
+shape of BASELINE.json configs[3]: --use_filter --check_right_edge, --nrec batching, subseq_length sweep.
+
+    python tools/cli_bench.py [--reads 100000] [--files 16] [--nrec 10000 100000] [--S 100 200 500] [--devices all]
+
+One JSON line per (nrec, S, devices) run: seconds from process start to summary.csv on disk (CUDA context, reader,
+scan, per-read FASTA.gz / density-vector files included), reads, bases, telomeric reads written."""
+import argparse
 import gzip
+import json
 import os
 import subprocess
 import sys
 import tempfile
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "telomere-analyzer_b200"))
-from nanotel_b200.synth import as_list, synth_reads  # noqa: E402
+from nanotel_b200.synth import synth_reads  # noqa: E402
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
-buf, off, meta = synth_reads(n, 20261022)
-seqs = as_list(buf, off)
+ap = argparse.ArgumentParser()
+ap.add_argument("--reads", type=int, default=100000)
+ap.add_argument("--files", type=int, default=16)
+ap.add_argument("--nrec", type=int, nargs="+", default=[10000, 100000])
+ap.add_argument("--S", type=int, nargs="+", default=[100])
+ap.add_argument("--devices", default=None)
+ap.add_argument("--no-filter", action="store_true")
+a = ap.parse_args()
+
+buf, off, meta = synth_reads(a.reads, 20261018 + 4, telomeric_frac=0.30)
 d = tempfile.mkdtemp(prefix="ntl_cli_")
-k = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 fq = os.path.join(d, "in")                              # -i takes a file or a directory of files
 os.makedirs(fq)
-for j in range(k):
+
+
+def write_part(j):
     with gzip.open(os.path.join(fq, "part%03d.fastq.gz" % j), "wb", compresslevel=1) as f:
-        for i in range(j * n // k, (j + 1) * n // k):
-            f.write(b"@read%08d\n" % i + seqs[i] + b"\n+\n" + b"I" * len(seqs[i]) + b"\n")
+        for i in range(j * a.reads // a.files, (j + 1) * a.reads // a.files):
+            s = buf[int(off[i]):int(off[i + 1])].tobytes()
+            f.write(b"@read%08d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")
+
+
+t0 = time.perf_counter()
+with ThreadPoolExecutor(max_workers=min(a.files, os.cpu_count() or 1)) as pool:
+    list(pool.map(write_part, range(a.files)))
+gz_bytes = sum(os.path.getsize(os.path.join(fq, f)) for f in os.listdir(fq))
+print(json.dumps({"generated": a.files, "gz_bytes": gz_bytes, "seconds": round(time.perf_counter() - t0, 1)}), flush=True)
 env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "telomere-analyzer_b200"))
-for rep in range(2):                                   # the second run finds the NVRTC cubin in the cache
-    out = os.path.join(d, "out%d" % rep)
-    t0 = time.perf_counter()
-    subprocess.run([sys.executable, "-m", "nanotel_b200", "-i", fq, "--save_path", out, "--patterns", "YYAGGG", "--rc"],
-                   env=env, check=True, stdout=subprocess.DEVNULL)
-    dt = time.perf_counter() - t0
-    kept = len(os.listdir(os.path.join(out, "reads"))) if os.path.isdir(os.path.join(out, "reads")) else 0
-    print("run %d: %.2f s for %d reads, %.3f Gbases (%d telomeric reads written): %.1f Mbases/s" % (
-        rep, dt, n, meta["bases"] / 1e9, kept, meta["bases"] / dt / 1e6))
+run = 0
+for S in a.S:
+    for nrec in a.nrec:
+        out = os.path.join(d, "out%d" % run); run += 1
+        cmd = [sys.executable, "-m", "nanotel_b200", "-i", fq, "--save_path", out, "--patterns", "TTAGGG",
+               "--subseq_length", str(S), "--nrec", str(nrec)]
+        if not a.no_filter:
+            cmd += ["--use_filter", "--check_right_edge"]
+        if a.devices:
+            cmd += ["--devices", a.devices]
+        t0 = time.perf_counter()
+        subprocess.run(cmd, env=env, check=True, stdout=subprocess.DEVNULL)
+        dt = time.perf_counter() - t0
+        kept = len(os.listdir(os.path.join(out, "reads"))) if os.path.isdir(os.path.join(out, "reads")) else 0
+        print(json.dumps({"nrec": nrec, "subseq_length": S, "devices": a.devices or "0", "filter": not a.no_filter,
+                          "seconds": round(dt, 2), "reads": a.reads, "gbases": round(meta["bases"] / 1e9, 3),
+                          "telomeric_reads_written": kept, "mbases_per_s": round(meta["bases"] / dt / 1e6, 1),
+                          "host_cores": os.cpu_count()}), flush=True)

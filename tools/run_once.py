@@ -14,15 +14,27 @@ ap.add_argument("--runs", type=int, default=4)
 ap.add_argument("--tvr", default=None)
 ap.add_argument("--patterns", default="YYAGGG")
 ap.add_argument("--no-jit", action="store_true")
+ap.add_argument("--use-filter", action="store_true")
+ap.add_argument("--right-edge", action="store_true")
+ap.add_argument("--no-rc", action="store_true")
+ap.add_argument("--subseq", type=int, default=100)
+ap.add_argument("--telomeric-frac", type=float, default=None)
+ap.add_argument("--seed", type=int, default=20261020)
 ap.add_argument("--n-frac", type=float, default=None, help="fraction of reads that carry N (they take the 4-bit path)")
 a = ap.parse_args()
-buf, off, meta = synth_reads(a.reads, 20261020, **({} if a.n_frac is None else {"n_frac": a.n_frac}))
-sc = Scanner(a.patterns, a.tvr, rc=True, jit=False if a.no_jit else None)
+kw = {}
+if a.n_frac is not None:
+    kw["n_frac"] = a.n_frac
+if a.telomeric_frac is not None:
+    kw["telomeric_frac"] = a.telomeric_frac
+buf, off, meta = synth_reads(a.reads, a.seed, **kw)
+sc = Scanner(a.patterns, a.tvr, 0.6, a.subseq, rc=not a.no_rc, use_filter=a.use_filter, right_edge=a.right_edge,
+             jit=False if a.no_jit else None)
 sc.pack_concat(buf, off)
 sc.upload()
 for _ in range(a.runs):
     sc.run()
 t = sc.timings()
 k = max(t["steps"], 1)
-print("scan_ms %.4f triage_ms %.4f locate_ms %.4f (triage + locate) candidates %d jit %d" % (
-    t["scan_ms"] / k, t["triage_ms"], t["locate_ms"] / k, t["candidates"], t["scan_is_jit"]))
+print("filter_ms %.4f scan_ms %.4f triage_ms %.4f locate_ms %.4f (triage + locate) candidates %d jit %d path %s" % (
+    t["filter_ms"] / k, t["scan_ms"] / k, t["triage_ms"] / k, t["locate_ms"] / k, t["candidates"], t["scan_is_jit"], sc.scan_path))

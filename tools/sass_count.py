@@ -9,7 +9,7 @@ lo, hi = int(sys.argv[2], 16), int(sys.argv[3], 16)
 skip = [tuple(int(x, 16) for x in a.split('-')) for a in sys.argv[4:]]
 c = collections.Counter()
 for l in L:
-    m = re.match(r'\s+/\*([0-9a-f]{4})\*/\s+(@!?U?P\d\s+)?(\S+)', l)
+    m = re.match(r'\s+/\*([0-9a-f]{4,6})\*/\s+(@!?U?P\d\s+)?(\S+)', l)
     if not m:
         continue
     a = int(m.group(1), 16)
