@@ -208,54 +208,6 @@ __device__ __noinline__ u32 warp_cov(const ReadView &rv, int t, int wbase, int l
     return cov & ntl_valid_word(w << 5, rv.L);          /* trim() to [1, L] */
 }
 
-/* bits of this lane's word that lie inside [lo, hi]; lane 0 is never used (see warp_cov) */
-__device__ __forceinline__ u32 lane_mask(int wbase, int lane, int lo, int hi)
-{
-    const int p0 = (wbase + lane) << 5;
-    int lb = lo - p0; if (lb < 0) lb = 0;
-    int hb = hi - p0; if (hb > 31) hb = 31;
-    if (hb < lb || lane == 0) return 0u;
-    return (NTL_FULL >> (31 - hb)) & (NTL_FULL << lb);
-}
-__device__ __forceinline__ int lanes_min(u32 bits, int wbase, int lane, int lo, int hi)
-{
-    const u32 m = bits & lane_mask(wbase, lane, lo, hi);
-    const int cand = m ? ((wbase + lane) << 5) + __ffs((int)m) - 1 : NTL_IMAX;
-    const int r = __reduce_min_sync(NTL_FULL, cand);
-    return r == NTL_IMAX ? NTL_NONE : r;
-}
-__device__ __forceinline__ int lanes_max(u32 bits, int wbase, int lane, int lo, int hi)
-{
-    const u32 m = bits & lane_mask(wbase, lane, lo, hi);
-    const int cand = m ? ((wbase + lane) << 5) + 31 - __clz((int)m) : -NTL_IMAX;
-    const int r = __reduce_max_sync(NTL_FULL, cand);
-    return r == -NTL_IMAX ? NTL_NONE : r;
-}
-__device__ __forceinline__ int lanes_popc(u32 bits, int wbase, int lane, int lo, int hi)
-{
-    return (int)__reduce_add_sync(NTL_FULL, (unsigned)__popc(bits & lane_mask(wbase, lane, lo, hi)));
-}
-
-/* covered positions of track t inside [lo, hi] (1 <= lo <= hi <= L), recomputed from the read, 992 per step */
-__device__ __noinline__ int local_count(const ReadView &rv, int t, int lo, int hi, int lane)
-{
-    if (rv.cwb != nullptr) {
-#pragma unroll 1
-        for (int slot = 0; slot < 2; slot++) {
-            const int wbc = rv.cwb[slot];                       /* lanes 1..31 hold words wbc + 1 .. wbc + 31 */
-            if (wbc != NTL_NONE && lo >= ((wbc + 1) << 5) && hi < ((wbc + 32) << 5))
-                return lanes_popc(rv.ccov[slot * 32 + lane], wbc, lane, lo, hi);
-        }
-    }
-    int total = 0;
-    for (int wb = (lo >> 5) - 1; ((wb + 1) << 5) <= hi; wb += 31) {
-        u32 hs;
-        const u32 cov = warp_cov(rv, t, wb, lane, &hs);
-        total += lanes_popc(cov, wb, lane, lo, hi);
-    }
-    return total;
-}
-
 /* =============================================================================================================
  * K4: edge filter (filter_reads / filter_density, NanoTel.R:2083-2163)
  * ============================================================================================================= */
@@ -349,28 +301,22 @@ __global__ void __launch_bounds__(256) ntl_items_kernel(const uint8_t *active, i
 }
 
 /* =============================================================================================================
- * K3: locator
+ * K3: locator.  ONE THREAD per (candidate read, track): the window state machines of the reference are sequential
+ * scans with data-dependent exits, and a candidate needs only a few hundred bases of locally recomputed coverage, so
+ * a warp per item spends its 32 lanes on the same scalar work (measured: 4 300 warp-instructions per item, 41 % issue
+ * utilisation, bound by dependent latency); per thread the same item is a few thousand scalar instructions, 32 items
+ * share every warp-instruction, and the lanes of a warp (neighbouring tracks of the same reads) follow similar paths.
  * ============================================================================================================= */
-/* one copy of the IEEE double division (a ~80-instruction sequence) for the whole locate kernel: code size is what
- * this kernel stalls on */
+/* one copy of the IEEE double division (a ~80-instruction sequence) for the whole locate kernel */
 __device__ __noinline__ double k3_div(double a, double b) { return a / b; }
 
 struct WinTab {                 /* the window table of one track (analyze_subtelos :737-764), never materialised */
     const uint16_t *cnt;        /* covered bases per block of SG positions (K2); window k = blocks k Q .. k Q + Q - 1, */
-    int n, nb, Q, S, L;         /* the last window = every remaining block (n windows, nb blocks)                     */
+    int n, nb, Q, SG, S, L;     /* the last window = every remaining block (n windows, nb blocks)                     */
     int thr_reg, thr_last;      /* smallest telomeric count of a regular window / of this read's last window */
-    bool any;                   /* at least one telomeric window on this track                                */
-    const u32 *bits;            /* class bits of all windows (1 = telomeric) in shared memory, or NULL        */
-    const double *dens;         /* dens[c] = (double)c / (double)S, filled on the host with that division     */
 };
 __device__ __forceinline__ int wt_start(const WinTab &w, int k) { return 1 + k * w.S; }
 __device__ __forceinline__ int wt_end(const WinTab &w, int k) { return k == w.n - 1 ? w.L : (k + 1) * w.S; }
-__device__ __forceinline__ double wt_density_of_count(const WinTab &w, int k, int count)
-{
-    /* get_sub_density (NanoTel.R:467): count / width in double; width-S windows read the quotient from a table */
-    const int width = wt_end(w, k) - wt_start(w, k) + 1;
-    return width == w.S ? w.dens[count] : k3_div((double)count, (double)width);
-}
 __device__ __forceinline__ int wt_count(const WinTab &w, int k)
 {
     if (w.Q == 1 && k < w.n - 1) return (int)w.cnt[k];
@@ -385,222 +331,321 @@ __device__ __forceinline__ bool wt_telo_count(const WinTab &w, int k, int count)
 {
     return count >= (k == w.n - 1 ? w.thr_last : w.thr_reg);
 }
-__device__ __forceinline__ bool wt_telo(const WinTab &w, int k)
+__device__ __forceinline__ double wt_density_of_count(const WinTab &w, int k, int count)
 {
-    if (!w.any) return false;
-    if (w.bits != nullptr) return (w.bits[k >> 5] >> (k & 31)) & 1u;
-    return wt_telo_count(w, k, wt_count(w, k));
+    /* get_sub_density (NanoTel.R:467): count / width in double */
+    return k3_div((double)count, (double)(wt_end(w, k) - wt_start(w, k) + 1));
 }
 
-/* First window at or after `cur` in direction dir (+1 / -1), not beyond i1, whose class bit equals `want`; i1 + dir if
- * there is none.  With the class bits in shared memory every lane looks at one word, so a step covers 1024 windows;
- * reads with more windows than fit there rebuild one word per step with a ballot. */
-__device__ __noinline__ int next_window(const WinTab &w, int cur, int i1, int dir, bool want, int lane)
+/* First telomeric window at or after k0 (n if none) / last telomeric window at or before k0 (-1 if none).  The
+ * reference's scans walk window by window; between two telomeric windows nothing happens but resets, so the walk may
+ * jump.  When a window is one block (Q == 1) the regular windows are skipped 32 at a time: four independent 16-byte
+ * loads of 8 counts (a read's block range starts on a multiple of 8 entries), two compares per pair of counts. */
+__device__ __forceinline__ bool pair_has_telo(u32 x, u32 thr16) { return (x << 16) >= thr16 || x >= thr16; }
+__device__ __forceinline__ bool quad_has_telo(const uint4 &v, u32 thr16)
 {
-    const int nw = (w.n + 31) >> 5;
-    const u32 flip = want ? 0u : NTL_FULL;
-    const bool par = w.bits != nullptr;
-    for (;;) {
-        if (dir > 0 ? cur > i1 : cur < i1) return i1 + dir;
-        const int off = par ? lane : 0;
-        const int wi = (cur >> 5) + dir * off;
-        u32 word = 0u;
-        if (par) { if (wi >= 0 && wi < nw) word = w.bits[wi] ^ flip; }
-        else {
-            const int k = (wi << 5) + lane;
-            word = __ballot_sync(NTL_FULL, k < w.n && wt_telo_count(w, k, wt_count(w, k < w.n ? k : 0))) ^ flip;
+    return pair_has_telo(v.x, thr16) || pair_has_telo(v.y, thr16) || pair_has_telo(v.z, thr16) || pair_has_telo(v.w, thr16);
+}
+
+__device__ __noinline__ int next_telo_fwd(const WinTab &w, int k0)
+{
+    const int n = w.n;
+    int k = k0 < 0 ? 0 : k0;
+    if (w.Q == 1) {
+        const int nr = n - 1;                                            /* regular windows 0 .. nr - 1 */
+        const u32 thr16 = (u32)w.thr_reg << 16;
+        while (k < nr && (k & 7)) { if ((int)w.cnt[k] >= w.thr_reg) return k; k++; }
+        const uint4 *cv = reinterpret_cast<const uint4 *>(w.cnt);
+        while (k + 32 <= nr) {
+            const uint4 v0 = __ldg(cv + (k >> 3)), v1 = __ldg(cv + (k >> 3) + 1), v2 = __ldg(cv + (k >> 3) + 2), v3 = __ldg(cv + (k >> 3) + 3);
+            if (quad_has_telo(v0, thr16) || quad_has_telo(v1, thr16) || quad_has_telo(v2, thr16) || quad_has_telo(v3, thr16)) break;
+            k += 32;
         }
-        if (off == 0) word &= dir > 0 ? (NTL_FULL << (cur & 31)) : (NTL_FULL >> (31 - (cur & 31)));
-        const u32 nz = par ? __ballot_sync(NTL_FULL, word != 0u) : (word != 0u ? 1u : 0u);
-        if (nz == 0u) {
-            const int adv = par ? 32 : 1;
-            cur = dir > 0 ? ((cur >> 5) + adv) << 5 : (((cur >> 5) - adv + 1) << 5) - 1;
+        while (k < nr) { if ((int)w.cnt[k] >= w.thr_reg) return k; k++; }
+        if (k == nr && nr >= 0 && wt_telo_count(w, nr, wt_count(w, nr))) return nr;
+        return n;
+    }
+    for (; k < n; k++) if (wt_telo_count(w, k, wt_count(w, k))) return k;
+    return n;
+}
+
+__device__ __noinline__ int next_telo_bwd(const WinTab &w, int k0)
+{
+    const int n = w.n;
+    int k = k0 >= n ? n - 1 : k0;
+    if (k < 0) return -1;
+    if (w.Q == 1) {
+        const u32 thr16 = (u32)w.thr_reg << 16;
+        if (k == n - 1) { if (wt_telo_count(w, k, wt_count(w, k))) return k; k--; }
+        while (k >= 0 && (k & 7) != 7) { if ((int)w.cnt[k] >= w.thr_reg) return k; k--; }
+        const uint4 *cv = reinterpret_cast<const uint4 *>(w.cnt);
+        while (k >= 31) {                                                /* windows k - 31 .. k, k % 8 == 7 */
+            const int g = k >> 3;
+            const uint4 v0 = __ldg(cv + g), v1 = __ldg(cv + g - 1), v2 = __ldg(cv + g - 2), v3 = __ldg(cv + g - 3);
+            if (quad_has_telo(v0, thr16) || quad_has_telo(v1, thr16) || quad_has_telo(v2, thr16) || quad_has_telo(v3, thr16)) break;
+            k -= 32;
+        }
+        while (k >= 0) { if ((int)w.cnt[k] >= w.thr_reg) return k; k--; }
+        return -1;
+    }
+    for (; k >= 0; k--) if (wt_telo_count(w, k, wt_count(w, k))) return k;
+    return -1;
+}
+
+/* find_telo_position (NanoTel.R:973-1077): forward scan for the first run of telomeric windows with in_a_row >= R
+ * and score >= T, then the backward scan for the end.  Windows are 0-based here; non-telomeric windows only reset
+ * the run state, so stretches of them are jumped over (next_telo_fwd / _bwd). */
+__device__ __noinline__ void find_telo_position(const WinTab &w, double R, double T, int *ps, int *pe)
+{
+    const int n = w.n;
+    double score = 0.0;
+    int start = -1, end = -1, in_a_row = 0;
+    int end_position = 0;                                                /* 1-based i + 1 (:1022) */
+    for (int k = 0; k < n;) {                                            /* :1003-1025 */
+        const int c = wt_count(w, k);
+        if (!wt_telo_count(w, k, c)) {
+            score = 0.0; start = -1; in_a_row = 0;
+            if (0.0 >= R && 0.0 >= T) { end_position = k + 2; break; }   /* never with the reference's R >= 3 */
+            k = next_telo_fwd(w, k + 1);
             continue;
         }
-        const int src = __ffs((int)nz) - 1;
-        if (par) word = __shfl_sync(NTL_FULL, word, src);
-        const int pos = (((cur >> 5) + dir * src) << 5) + (dir > 0 ? __ffs((int)word) - 1 : 31 - __clz((int)word));
-        return (dir > 0 ? pos > i1 : pos < i1) ? i1 + dir : pos;
+        in_a_row += 1;
+        score = score + wt_density_of_count(w, k, c);                    /* :1014 */
+        if (start == -1) start = wt_start(w, k);
+        if ((double)in_a_row >= R && score >= T) { end_position = k + 2; break; }
+        k++;
     }
-}
-
-/* The run/score machine of find_telo_position (NanoTel.R:1003-1025 forward, :1046-1068 backward) over windows
- * i0, i0+dir, ..., i1 (0-based, inclusive).  Returns the window index at which  in_a_row >= R && score >= T  first
- * holds, or -1; *first = first window of the run that is open when the scan stops (-1 if none).
- * in_a_row and score restart at every non-telomeric window, so the machine is evaluated run by run: runs are found
- * with next_window(), runs shorter than R are skipped without touching their densities, and the fp64 score of a
- * longer run is summed in window order (lanes fetch 32 densities at a time, the sum itself is sequential as in R). */
-__device__ __noinline__ int run_scan(const WinTab &w, int i0, int i1, int dir, double R, double T, int *first, int lane)
-{
-    int need = (int)R;
-    if ((double)need < R) need += 1;                     /* in_a_row >= R for an integer in_a_row */
-    int cur = i0;
-    for (;;) {
-        const int a = next_window(w, cur, i1, dir, true, lane);
-        if (a == i1 + dir) { *first = -1; return -1; }
-        const int b = next_window(w, a + dir, i1, dir, false, lane);
-        const int len = (b - a) * dir;
-        if (len >= need) {
-            double score = 0.0;
-            for (int j0 = 0; j0 < len; j0 += 32) {
-                const int k = a + (j0 + lane) * dir;
-                double d = 0.0;
-                if (j0 + lane < len) d = wt_density_of_count(w, k, wt_count(w, k));
-                const int m = len - j0 < 32 ? len - j0 : 32;
-                for (int j = 0; j < m; j++) {
-                    score = score + __shfl_sync(NTL_FULL, d, j);                 /* :1014 */
-                    if (j0 + j + 1 >= need && score >= T) { *first = a; return a + (j0 + j) * dir; }
-                }
-            }
-        }
-        if (b == i1 + dir) { *first = a; return -1; }   /* the scan ends inside this run */
-        cur = b + dir;
-    }
-}
-
-/* find_telo_position (NanoTel.R:973-1077) */
-__device__ __noinline__ void find_telo_position(const WinTab &w, double R, double T, int *ps, int *pe, int lane)
-{
-    const int n = w.n;
-    int first = -1;
-    int hit = (n > 0 && w.any) ? run_scan(w, 0, n - 1, +1, R, T, &first, lane) : -1;
-    if (hit < 0) { *ps = -1; *pe = -1; return; }                         /* :1026-1028 */
-    const int start = wt_start(w, first);
-    const int end_position = hit + 2;                                    /* 1-based i + 1 (:1022) */
-    int end;
+    if (end_position == 0) { *ps = -1; *pe = -1; return; }               /* :1026-1028 */
+    end = -1; score = 0.0; in_a_row = 0;
     if ((double)end_position >= (double)n - R + 1.0) {                   /* :1037-1044 */
-        /* i = n; while (i > end_position && window i is not telomeric) i--  (1-based): the last telomeric window
-         * among 0-based end_position .. n-1, else end_position - 1 */
-        const int j = next_window(w, n - 1, end_position, -1, true, lane);
-        end = wt_end(w, j < n - 1 ? j : n - 1);          /* end_position may be n + 1: the loop does not run */
+        /* i = n; while (i > end_position && window i is not telomeric) i--  (1-based) */
+        int i = next_telo_bwd(w, n - 1) + 1;                             /* 1-based, 0 if none */
+        if (i < end_position) i = end_position;
+        end = wt_end(w, (i < n ? i : n) - 1);                            /* end_position may be n + 1: the loop does not run */
     } else {                                                             /* :1046-1068 */
-        int bfirst = -1;
-        run_scan(w, n - 1, end_position - 1, -1, R, T, &bfirst, lane);
-        end = bfirst >= 0 ? wt_end(w, bfirst) : -1;
+        for (int i = n; i >= end_position;) {
+            const int c = wt_count(w, i - 1);
+            if (!wt_telo_count(w, i - 1, c)) {
+                score = 0.0; end = -1; in_a_row = 0;
+                const int j = next_telo_bwd(w, i - 2) + 1;               /* 1-based */
+                i = j;
+                continue;
+            }
+            in_a_row += 1;
+            score = score + wt_density_of_count(w, i - 1, c);
+            if (end == -1) end = wt_end(w, i - 1);
+            if ((double)in_a_row >= R && score >= T) break;
+            i--;
+        }
     }
-    if (start > end) end = start + (wt_end(w, 0) - wt_start(w, 0));       /* :1072-1074 */
+    if (start > end) end = start + (wt_end(w, 0) - wt_start(w, 0));      /* :1072-1074 */
     *ps = start; *pe = end;
 }
 
-/* find_left_telo (NanoTel.R:906-959) and find_right_telo (NanoTel.R:843-899) are mirror images: walk from the chosen
- * edge (right = false: window 0 upward, true: window n-1 downward) to the first telomeric window, give up as soon as
- * a window lies more than max_diff = 200 from that edge, then extend over the telomeric run.  n == 0 with the right
- * edge is the caller's REF_ERROR case. */
-__device__ __noinline__ void find_edge_telo(const WinTab &w, bool right, int *ps, int *pe, int lane)
+/* find_left_telo (NanoTel.R:906-959): walk from window 0 to the first telomeric window, give up as soon as a window
+ * starts more than max_diff = 200 from the edge, then extend over the telomeric run. */
+__device__ __noinline__ void find_left_telo(const WinTab &w, int *ps, int *pe)
 {
     const int n = w.n;
-    if (!w.any) {                       /* no telomeric window anywhere: only the max_diff test can fire */
-        const bool far = n > 0 && (right ? wt_end(w, 0) < w.L - 200 : wt_start(w, n - 1) > 200);
-        *ps = far ? -1 : 1; *pe = far ? -1 : 1;
-        return;
-    }
-    const int dir = right ? -1 : 1;
     int start = 1, end = 1, last_i = 0;
-    for (int i = right ? n - 1 : 0; i >= 0 && i < n; i += dir) {
-        if (right ? wt_end(w, i) < w.L - 200 : wt_start(w, i) > 200) { *ps = -1; *pe = -1; return; }
-        if (!wt_telo(w, i)) continue;
-        if (right) end = wt_end(w, i); else start = wt_start(w, i);
-        last_i = i;
-        break;
+    for (int i = 0; i < n; i++) {
+        if (wt_start(w, i) > 200) { *ps = -1; *pe = -1; return; }
+        if (!wt_telo_count(w, i, wt_count(w, i))) continue;
+        start = wt_start(w, i); last_i = i; break;
     }
-    const int anchor = last_i;          /* find_left_telo keeps last_i_start (:937), find_right_telo moves last_i (:886) */
-    if (wt_telo(w, last_i)) {           /* extend over the run of telomeric windows that starts at last_i */
-        const int lim = right ? 0 : n - 1;
-        const int last = next_window(w, last_i, lim, dir, false, lane) - dir;
-        if (right) { start = wt_start(w, last); last_i = last; } else end = wt_end(w, last);
+    const int last_i_start = last_i;
+    for (int i = last_i; i < n; i++) {
+        if (!wt_telo_count(w, i, wt_count(w, i))) break;
+        end = wt_end(w, i);
     }
-    const int ref = right ? last_i : anchor;
-    if (start > end) end = start + (wt_end(w, ref) - wt_start(w, ref));
+    if (start > end && n > 0) end = start + (wt_end(w, last_i_start) - wt_start(w, last_i_start));
     *ps = start; *pe = end;
 }
 
-/* covered bases of track t inside [a, b] (get_sub_density's numerator, NanoTel.R:467): whole windows come from
- * K2's prefixes, partial windows are recomputed from the read. */
-__device__ __noinline__ int covered_in(const ReadView &rv, const WinTab &w, int t, int a, int b, int lane)
+/* find_right_telo (NanoTel.R:843-899); n == 0 is the caller's REF_ERROR case */
+__device__ __noinline__ void find_right_telo(const WinTab &w, int *ps, int *pe)
+{
+    const int n = w.n;
+    int start = 1, end = 1, last_i = 0;
+    for (int i = n - 1; i >= 0; i--) {
+        if (wt_end(w, i) < w.L - 200) { *ps = -1; *pe = -1; return; }
+        if (!wt_telo_count(w, i, wt_count(w, i))) continue;
+        end = wt_end(w, i); last_i = i; break;
+    }
+    for (int i = last_i; i >= 0; i--) {
+        if (!wt_telo_count(w, i, wt_count(w, i))) break;
+        start = wt_start(w, i); last_i = i;
+    }
+    if (start > end) end = start + (wt_end(w, last_i) - wt_start(w, last_i));
+    *ps = start; *pe = end;
+}
+
+/* Coverage of track t (0 exact, 1 one mismatch, 2 one mismatch + TVR; the union of the trimmed hit intervals of
+ * get_density_iranges, NanoTel.R:308-397) for virtual words w0 .. w0 + nw - 1 (bit b of word w = position 32 w + b),
+ * recomputed from the packed read by ONE thread: the hit starts of every pattern in (previous word, word) dilated by
+ * the pattern length.  hs (optional): exact hit starts of main pattern 0 for words w0 - 1 .. w0 + nw - 1 (nw + 1
+ * entries: the raw hit list of NanoTel.R:349-354). */
+#define NTL_COV_MAXW 8
+__device__ __noinline__ void cov_words(const ReadView &rv, int t, int w0, int nw, u32 *cov, u32 *hs)
+{
+    u32 prevH[2 * NTL_DEV_MAX_PAT];
+    u32 pc[4], pn[4];
+    const int np_main = c_prm.n_main, np_tvr = t == 2 ? c_prm.n_tvr : 0;
+    /* hits of word w0 - 1 first */
+    word_planes(rv, w0 - 1, pc);
+    word_planes(rv, w0, pn);
+    for (int p = 0; p < np_main + np_tvr; p++) {
+        const ntl_dev_pat &pt = p < np_main ? c_prm.main_pat[p] : c_prm.tvr_pat[p - np_main];
+        u32 ex, le;
+        word_hits(pt, pc, pn, &ex, &le);
+        prevH[p] = (p < np_main && t >= 1) ? le : ex;
+        if (p == 0 && hs) hs[0] = ex;
+    }
+    for (int i = 0; i < nw; i++) {
+        const int w = w0 + i;
+#pragma unroll
+        for (int k = 0; k < 4; k++) pc[k] = pn[k];
+        word_planes(rv, w + 1, pn);
+        u32 c = 0u;
+        for (int p = 0; p < np_main + np_tvr; p++) {
+            const ntl_dev_pat &pt = p < np_main ? c_prm.main_pat[p] : c_prm.tvr_pat[p - np_main];
+            u32 ex, le;
+            word_hits(pt, pc, pn, &ex, &le);
+            const u32 H = (p < np_main && t >= 1) ? le : ex, Hp = prevH[p];
+            if (p == 0 && hs) hs[i + 1] = ex;
+            for (int j = 0; j < pt.m; j++) c |= __funnelshift_l(Hp, H, j);
+            prevH[p] = H;
+        }
+        cov[i] = (w < 0 || w >= rv.n_words) ? 0u : (c & ntl_valid_word(w << 5, rv.L));     /* trim() to [1, L] */
+    }
+}
+
+/* bits of virtual word w that lie inside positions [lo, hi] */
+__device__ __forceinline__ u32 word_range_mask(int w, int lo, int hi)
+{
+    const int p0 = w << 5;
+    int lb = lo - p0; if (lb < 0) lb = 0;
+    int hb = hi - p0; if (hb > 31) hb = 31;
+    return hb < lb ? 0u : ((NTL_FULL >> (31 - hb)) & (NTL_FULL << lb));
+}
+
+/* covered positions of track t inside [lo, hi] (1 <= lo <= hi <= L), recomputed from the read */
+__device__ __noinline__ int local_count(const ReadView &rv, int t, int lo, int hi)
+{
+    int total = 0;
+    for (int w0 = lo >> 5; w0 <= (hi >> 5); w0 += NTL_COV_MAXW) {
+        u32 cov[NTL_COV_MAXW];
+        const int nw = (hi >> 5) - w0 + 1 < NTL_COV_MAXW ? (hi >> 5) - w0 + 1 : NTL_COV_MAXW;
+        cov_words(rv, t, w0, nw, cov, nullptr);
+        for (int i = 0; i < nw; i++) total += __popc(cov[i] & word_range_mask(w0 + i, lo, hi));
+    }
+    return total;
+}
+
+/* covered bases of track t inside [a, b] (get_sub_density's numerator, NanoTel.R:467): whole blocks come from K2's
+ * counts, the partial blocks at the two ends are recomputed from the read. */
+__device__ __noinline__ int covered_in(const ReadView &rv, const WinTab &w, int t, int a, int b)
 {
     const int lo = a < 1 ? 1 : a, hi = b > rv.L ? rv.L : b;
     if (hi < lo) return 0;
-    if (w.n <= 0) return local_count(rv, t, lo, hi, lane);
-    int klo = (lo - 1) / w.S; if (klo > w.n - 1) klo = w.n - 1;
-    int khi = (hi - 1) / w.S; if (khi > w.n - 1) khi = w.n - 1;
-    if (klo == khi) {
-        if (lo == wt_start(w, klo) && hi == wt_end(w, klo)) return wt_count(w, klo);
-        return local_count(rv, t, lo, hi, lane);
+    const int SG = w.SG;
+    const int blo = (lo - 1) / SG, bhi = (hi - 1) / SG;
+    /* block j = positions [j SG + 1, min((j + 1) SG, L)] */
+    const int blo_s = blo * SG + 1, bhi_e = (bhi + 1) * SG < rv.L ? (bhi + 1) * SG : rv.L;
+    if (blo == bhi) {
+        if (lo == blo_s && hi == bhi_e) return (int)w.cnt[blo];
+        return local_count(rv, t, lo, hi);
     }
-    int total = 0, kf = klo, kl = khi;
-    if (lo != wt_start(w, klo)) { total += local_count(rv, t, lo, wt_end(w, klo), lane); kf = klo + 1; }
-    if (hi != wt_end(w, khi)) { total += local_count(rv, t, wt_start(w, khi), hi, lane); kl = khi - 1; }
-    /* whole windows kf .. kl: their blocks, 32 at a time */
-    int part = 0;
-    const int b0 = kf * w.Q, b1 = kl == w.n - 1 ? w.nb : (kl + 1) * w.Q;
-    for (int b = b0 + lane; b < b1; b += 32) part += (int)w.cnt[b];
-    return total + (int)__reduce_add_sync(NTL_FULL, (unsigned)part);
+    int total = 0, bf = blo, bl = bhi;
+    if (lo != blo_s) { total += local_count(rv, t, lo, (blo + 1) * SG); bf = blo + 1; }
+    if (hi != bhi_e) { total += local_count(rv, t, bhi * SG + 1, hi); bl = bhi - 1; }
+    for (int j = bf; j <= bl; j++) total += (int)w.cnt[j];
+    return total;
 }
 
-__device__ __forceinline__ double density_of(const ReadView &rv, const WinTab &w, int t, int a, int b, int lane)
+__device__ __forceinline__ double density_of(const ReadView &rv, const WinTab &w, int t, int a, int b)
 {
-    const int cv = covered_in(rv, w, t, a, b, lane);
+    const int cv = covered_in(rv, w, t, a, b);
     return cv == 0 ? 0.0 : k3_div((double)cv, (double)(b - a + 1));      /* 0 / width is +0.0 exactly */
+}
+
+/* largest / smallest position of a set bit of bits[0 .. nw) (virtual words w0 ..) inside [lo, hi]; NTL_NONE if none */
+__device__ __forceinline__ int bits_max_in(const u32 *bits, int w0, int nw, int lo, int hi)
+{
+    for (int i = nw - 1; i >= 0; i--) {
+        const u32 m = bits[i] & word_range_mask(w0 + i, lo, hi);
+        if (m) return ((w0 + i) << 5) + 31 - __clz((int)m);
+    }
+    return NTL_NONE;
+}
+__device__ __forceinline__ int bits_min_in(const u32 *bits, int w0, int nw, int lo, int hi)
+{
+    for (int i = 0; i < nw; i++) {
+        const u32 m = bits[i] & word_range_mask(w0 + i, lo, hi);
+        if (m) return ((w0 + i) << 5) + __ffs((int)m) - 1;
+    }
+    return NTL_NONE;
 }
 
 /* get_accurate_end (NanoTel.R:1692-1721).  `ranges` are the raw exact hits of the single fixed pattern on track A
  * (NanoTel.R:349-354) and the reduced runs of the coverage otherwise (:341-345). */
-__device__ __noinline__ int get_accurate_end(const ReadView &rv, int t, int telo_end, int lane)
+__device__ __noinline__ int get_accurate_end(const ReadView &rv, int t, int telo_end)
 {
     if (telo_end == -1) return -1;
-    /* lanes 1.. cover [e-99, e+51]; the block starts early enough to hold the window of the final end as well */
-    const int wb = ((telo_end - 99 - 160) >> 5) - 1;
-    u32 hs;
-    const u32 cov = warp_cov(rv, t, wb, lane, &hs);
-    rv.ccov[32 + lane] = cov;
-    if (lane == 0) rv.cwb[1] = wb;
-    __syncwarp();
-    u32 en;
+    /* range ends inside [e - 99, e + 50]: coverage of the words holding [e - 99, e + 51] */
+    const int w0 = (telo_end - 99) >> 5;
+    const int nw = ((telo_end + 51) >> 5) - w0 + 1;                      /* <= 6 */
+    u32 cov[NTL_COV_MAXW], hs[NTL_COV_MAXW + 1], en[NTL_COV_MAXW];
+    cov_words(rv, t, w0, nw, cov, hs);
     if (t == 0 && c_prm.raw_hits_A) {
-        const u32 hp = __shfl_up_sync(NTL_FULL, hs, 1);
-        en = __funnelshift_l(hp, hs, c_prm.main_pat[0].m - 1);
+        const int m = c_prm.main_pat[0].m;
+        for (int i = 0; i < nw; i++) en[i] = __funnelshift_l(hs[i], hs[i + 1], m - 1);      /* end = start + m - 1 */
     } else {
-        const u32 nx = __shfl_down_sync(NTL_FULL, cov, 1);
-        en = cov & ~((cov >> 1) | (nx << 31));
+        for (int i = 0; i < nw; i++) {
+            const u32 nx = i + 1 < nw ? cov[i + 1] : 0u;                 /* the last word is only the look-ahead */
+            en[i] = cov[i] & ~((cov[i] >> 1) | (nx << 31));
+        }
     }
     int e_index = telo_end;
-    const int m1 = lanes_max(en, wb, lane, telo_end - 99, telo_end);
+    const int m1 = bits_max_in(en, w0, nw, telo_end - 99, telo_end);
     if (m1 != NTL_NONE) e_index = m1;
-    const int m2 = lanes_max(en, wb, lane, telo_end + 1, telo_end + 50);
+    const int m2 = bits_max_in(en, w0, nw, telo_end + 1, telo_end + 50);
     if (m2 != NTL_NONE) e_index = m2;
     return e_index;
 }
 
 /* get_accurate_start (NanoTel.R:1726-1764) */
-__device__ __noinline__ int get_accurate_start(const ReadView &rv, int t, int telo_start, int lane)
+__device__ __noinline__ int get_accurate_start(const ReadView &rv, int t, int telo_start)
 {
     if (telo_start == -1) return telo_start;
     const int s = telo_start;
-    /* lanes 1.. cover [s-37, s+100]; the block starts early enough to hold the final start (search_left) as well */
-    const int wb = ((s - 37 - 64) >> 5) - 1;
-    u32 hs;
-    const u32 cov = warp_cov(rv, t, wb, lane, &hs);
-    rv.ccov[lane] = cov;
-    if (lane == 0) rv.cwb[0] = wb;
-    __syncwarp();
-    u32 st;
-    if (t == 0 && c_prm.raw_hits_A) st = hs;
-    else {
-        const u32 pv = __shfl_up_sync(NTL_FULL, cov, 1);
-        st = cov & ~((cov << 1) | (pv >> 31));
+    /* range starts inside [s - 36, s + 99]: coverage of the words holding [s - 37, s + 99] */
+    const int w0 = (s - 37) >> 5;
+    const int nw = ((s + 99) >> 5) - w0 + 1;                             /* <= 6 */
+    u32 cov[NTL_COV_MAXW], hs[NTL_COV_MAXW + 1], st[NTL_COV_MAXW];
+    cov_words(rv, t, w0, nw, cov, hs);
+    if (t == 0 && c_prm.raw_hits_A) {
+        for (int i = 0; i < nw; i++) st[i] = hs[i + 1];
+    } else {
+        for (int i = 0; i < nw; i++) {
+            const u32 pv = i > 0 ? cov[i - 1] : 0u;                      /* the first word is only the look-behind */
+            st[i] = cov[i] & ~((cov[i] << 1) | (pv >> 31));
+        }
     }
-    const int c50 = lanes_popc(cov, wb, lane, s, s + 49);
+    int c50 = 0;
+    for (int i = 0; i < nw; i++) c50 += __popc(cov[i] & word_range_mask(w0 + i, s, s + 49));
     const double first_50 = k3_div((double)c50, 50.0);                         /* IRanges(start, width = 50) :1732 */
+    /* the look-behind word: range starts are only asked for at positions >= s - 36 > 32 w0 + 31 - 32 ... see below */
     if (first_50 < 0.3) {
-        const int a = lanes_min(st, wb, lane, s + 48, s + 99);
+        const int a = bits_min_in(st, w0, nw, s + 48, s + 99);
         if (a != NTL_NONE) telo_start = a;
-        const int b = lanes_min(st, wb, lane, s + 33, s + 48);
+        const int b = bits_min_in(st, w0, nw, s + 33, s + 48);
         if (b != NTL_NONE) telo_start = b;
     } else {
-        const int a = lanes_min(st, wb, lane, s, s + 99);
+        const int a = bits_min_in(st, w0, nw, s, s + 99);
         if (a != NTL_NONE) telo_start = a;
         if (first_50 >= 0.72) {
-            const int b = lanes_min(st, wb, lane, s - 36, s - 1);
+            const int b = bits_min_in(st, w0, nw, s - 36, s - 1);
             if (b != NTL_NONE) telo_start = b;
         }
     }
@@ -673,7 +718,7 @@ __device__ __noinline__ bool step_window(const ReadView &rv, int a, int b, int k
 }
 
 /* search_left_patterns (NanoTel.R:576-633) */
-__device__ __noinline__ int search_left(const ReadView &rv, int start_index, int k, bool use_tvr, int lane)
+__device__ __noinline__ int search_left(const ReadView &rv, int start_index, int k, bool use_tvr)
 {
     int subseq_start = start_index - 18 > 1 ? start_index - 18 : 1;
     int new_start = start_index;
@@ -690,7 +735,7 @@ __device__ __noinline__ int search_left(const ReadView &rv, int start_index, int
 }
 
 /* search_right_patterns (NanoTel.R:635-697) */
-__device__ __noinline__ int search_right(const ReadView &rv, int end_index, int k, bool use_tvr, int lane)
+__device__ __noinline__ int search_right(const ReadView &rv, int end_index, int k, bool use_tvr)
 {
     int subseq_end = end_index + 18 < rv.L ? end_index + 18 : rv.L;
     int new_end = end_index;
@@ -864,184 +909,111 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
 }
 
 /* =============================================================================================================
- * K3b: full locator, one WARP per candidate read (persistent grid, dynamic work counter)
+ * K3b: full locator, one THREAD per (candidate read, track); the thread that completes a read's last track writes
+ * the record head.
  * ============================================================================================================= */
-#define NTL_BITS_WORDS 512          /* class bits of up to 16384 windows per warp in shared memory */
-
-__device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *state, int lane, u32 *sbits, u32 *ccov, int *cwb);
-
-__global__ void __launch_bounds__(128, 8) ntl_locate_kernel(const ntl_read_args a)
-{
-    __shared__ u32 s_bits[4][NTL_BITS_WORDS];
-    __shared__ u32 s_ccov[4][64];
-    __shared__ int s_cwb[4][2];
-    const int lane = threadIdx.x & 31;
-    /* work item = (candidate read, track): the tracks of a read are independent until the keep rule, so they run
-     * on different warps; cand_state[c] = {tracks done, width (or -1: error) of track 0, 1, 2} joins them */
-    const int T = c_prm.n_tracks;
-    const int n_items = (int)a.counters[0] * T;
-    for (;;) {
-        int i = 0;
-        if (lane == 0) i = (int)atomicAdd(&a.counters[1], 1u);
-        i = __shfl_sync(NTL_FULL, i, 0);
-        if (i >= n_items) break;
-        const int c = i / T;
-        locate_read(a, a.cand[c], i - c * T, a.cand_state + 4 * (size_t)c, lane, s_bits[threadIdx.x >> 5],
-                    s_ccov[threadIdx.x >> 5], s_cwb[threadIdx.x >> 5]);
-    }
-}
-
-/* any window of this track with  !(count / width < min_density)?  Also leaves the class bits (1 = telomeric
- * window) in bits[] (shared memory, one warp) when it is given.  A window that is one block (Q == 1): 256 counts per
- * warp-wide 16-byte load (a read's block range starts on a multiple of 8 entries), lane l holds windows 8 l .. 8 l + 7,
- * four lanes make one 32-bit word; else one window per lane. */
-__device__ __noinline__ bool warp_any_telomeric(const WinTab &w, int lane, u32 *bits)
-{
-    bool tel = false;
-    if (w.Q == 1) {
-        const uint4 *cv = reinterpret_cast<const uint4 *>(w.cnt);
-        const int groups = (w.n + 7) >> 3;
-        const u32 thr16 = (u32)w.thr_reg << 16;
-        for (int g0 = 0; g0 < groups; g0 += 32) {
-            const int g = g0 + lane;
-            u32 b8 = 0u;
-            if (g < groups) {
-                const uint4 v = __ldg(cv + g);
-                const u32 x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if ((x[q] << 16) >= thr16) b8 |= 1u << (2 * q);
-                    if (x[q] >= thr16) b8 |= 2u << (2 * q);
-                }
-                const int kl = w.n - 1 - 8 * g;            /* the read's last window (own width: it takes every block left) */
-                if (kl < 8) {
-                    b8 &= (1u << kl) - 1u;
-                    if (wt_telo_count(w, w.n - 1, wt_count(w, w.n - 1))) b8 |= 1u << kl;
-                }
-            }
-            tel |= b8 != 0u;
-            if (bits != nullptr) {
-                u32 wd = b8 << (8 * (lane & 3));
-                wd |= __shfl_xor_sync(NTL_FULL, wd, 1);
-                wd |= __shfl_xor_sync(NTL_FULL, wd, 2);
-                if ((lane & 3) == 0 && g < groups) bits[g >> 2] = wd;
-            }
-        }
-        __syncwarp();
-        return __any_sync(NTL_FULL, tel);
-    }
-    for (int k0 = 0; k0 < w.n; k0 += 32) {
-        const int k = k0 + lane;
-        const bool t = k < w.n && wt_telo_count(w, k, wt_count(w, k));
-        const u32 word = __ballot_sync(NTL_FULL, t);
-        tel |= word != 0u;
-        if (bits != nullptr && lane == 0) bits[k0 >> 5] = word;
-    }
-    __syncwarp();
-    return tel;
-}
-
-__device__ void locate_read(const ntl_read_args &a, int r, int t_only, int *state, int lane, u32 *sbits, u32 *ccov, int *cwb)
+__device__ void locate_item(const ntl_read_args &a, int r, int t, int *state)
 {
     ntl_read_result *res = reinterpret_cast<ntl_read_result *>(a.results) + r;
     ntl_stage *stg = a.stages ? reinterpret_cast<ntl_stage *>(a.stages) + (size_t)r * 3 : nullptr;
 
     ReadView rv;
     rv_init(rv, a, r);
-    rv.ccov = ccov; rv.cwb = cwb;
-    __syncwarp();                                                   /* the previous item is done with the cache */
-    if (lane < 2) cwb[lane] = NTL_NONE;
-    __syncwarp();
     const int S = c_prm.S, T = c_prm.n_tracks;
     const int n_win = ntl_nwin(rv.L, S);
     int status = rv.fmt ? NTL_READ_IUPAC : 0;
     if (n_win <= 0) status |= NTL_READ_NO_WINDOWS;
 
-    ntl_track out[3];
-    for (int t = 0; t < 3; t++) { out[t].start = 0; out[t].end = 0; out[t].density = 0.0; }
+    ntl_track out;
+    out.start = 0; out.end = 0; out.density = 0.0;
+    bool err = false;
+    int width = 0;
+    {
+        WinTab w;
+        w.cnt = a.cnt[t] + a.cnt_off[r]; w.n = n_win > 0 ? n_win : 0; w.S = S; w.L = rv.L;
+        w.Q = c_prm.Q; w.SG = c_prm.SG; w.nb = (rv.L + c_prm.SG - 1) / c_prm.SG;
+        w.thr_reg = c_prm.thr_reg;
+        w.thr_last = w.n > 0 ? (int)a.thr[wt_end(w, w.n - 1) - wt_start(w, w.n - 1) + 1] : 0;
+        const int k = t >= 1 ? 1 : 0;
+        const bool use_tvr = t == 2;
 
-    if (a.pass != nullptr && a.pass[r] == 0) {
-        status |= NTL_READ_FILTERED;
-    } else {
-        bool err = false;
-        int max_width = 0;
-        for (int t = t_only; t == t_only; t++) {
-            WinTab w;
-            w.cnt = a.cnt[t] + a.cnt_off[r]; w.n = n_win > 0 ? n_win : 0; w.S = S; w.L = rv.L;
-            w.Q = c_prm.Q; w.nb = (rv.L + c_prm.SG - 1) / c_prm.SG;
-            w.thr_reg = c_prm.thr_reg;
-            w.dens = a.dens;
-            w.thr_last = w.n > 0 ? (int)a.thr[wt_end(w, w.n - 1) - wt_start(w, w.n - 1) + 1] : 0;
-            w.bits = nullptr;
-            __syncwarp();                                           /* the previous track is done with sbits */
-            u32 *bits = w.n <= NTL_BITS_WORDS * 32 ? sbits : nullptr;
-            w.any = w.n > 0 && warp_any_telomeric(w, lane, bits);
-            w.bits = bits;
-            const int k = t >= 1 ? 1 : 0;
-            const bool use_tvr = t == 2;
-
-            int ts, te;
-            find_telo_position(w, 3.0, 2.0, &ts, &te, lane);                               /* :1084-1086 */
-            const double telo_density = density_of(rv, w, t, ts, te, lane);                /* :1099 */
-            const int num_rows = (te - ts + 1) / S;                                        /* :1103 */
-            if (telo_density < 0.85 && num_rows > 5) {                                     /* :1104-1110 */
-                const double min_rows = num_rows <= 7 ? (double)(num_rows - 2) : 7.0;
-                const double min_score = 0.6 * min_rows;
-                find_telo_position(w, min_rows, min_score, &ts, &te, lane);
-            }
-            const int cs = ts, ce = te;
-            int start_acc = get_accurate_start(rv, t, ts, lane);                           /* :1119 */
-            int end_acc = get_accurate_end(rv, t, te, lane);                               /* :1120 */
-            if (start_acc > end_acc) end_acc = start_acc;                                  /* :1122-1124 */
-            ts = start_acc; te = end_acc;
-            const int as = ts, ae = te;
-            double acc_density = 0.0;
-            if (stg) acc_density = density_of(rv, w, t, ts, te, lane);
-            if (te - ts + 1 < 100) {                                                       /* :1129-1136 */
-                if (c_prm.right_edge) {
-                    if (w.n == 0) { err = true; break; }                                   /* R stops at :859-861 */
-                    find_edge_telo(w, true, &ts, &te, lane);
-                } else find_edge_telo(w, false, &ts, &te, lane);
-            }
-            if (stg && lane == 0) {
-                ntl_stage s;
-                s.coarse_start = cs; s.coarse_end = ce; s.acc_start = as; s.acc_end = ae;
-                s.edge_start = ts; s.edge_end = te; s.acc_density = acc_density;
-                stg[t] = s;
+        int ts, te;
+        find_telo_position(w, 3.0, 2.0, &ts, &te);                                     /* :1084-1086 */
+        const double telo_density = density_of(rv, w, t, ts, te);                      /* :1099 */
+        const int num_rows = (te - ts + 1) / S;                                        /* :1103 */
+        if (telo_density < 0.85 && num_rows > 5) {                                     /* :1104-1110 */
+            const double min_rows = num_rows <= 7 ? (double)(num_rows - 2) : 7.0;
+            const double min_score = 0.6 * min_rows;
+            find_telo_position(w, min_rows, min_score, &ts, &te);
+        }
+        const int cs = ts, ce = te;
+        int start_acc = get_accurate_start(rv, t, ts);                                 /* :1119 */
+        int end_acc = get_accurate_end(rv, t, te);                                     /* :1120 */
+        if (start_acc > end_acc) end_acc = start_acc;                                  /* :1122-1124 */
+        ts = start_acc; te = end_acc;
+        const int as = ts, ae = te;
+        double acc_density = 0.0;
+        if (stg) acc_density = density_of(rv, w, t, ts, te);
+        if (te - ts + 1 < 100) {                                                       /* :1129-1136 */
+            if (c_prm.right_edge) {
+                if (w.n == 0) err = true;                                              /* R stops at :859-861 */
+                else find_right_telo(w, &ts, &te);
+            } else find_left_telo(w, &ts, &te);
+        }
+        if (!err) {
+            if (stg) {
+                ntl_stage sg;
+                sg.coarse_start = cs; sg.coarse_end = ce; sg.acc_start = as; sg.acc_end = ae;
+                sg.edge_start = ts; sg.edge_end = te; sg.acc_density = acc_density;
+                stg[t] = sg;
             }
             int e2, s2;
-            if (te < rv.L) e2 = search_right(rv, te + 1, k, use_tvr, lane);                /* :1140-1144 */
+            if (te < rv.L) e2 = search_right(rv, te + 1, k, use_tvr);                  /* :1140-1144 */
             else e2 = te;
-            if (ts > 1) s2 = search_left(rv, ts - 1, k, use_tvr, lane);                    /* :1145-1149 */
+            if (ts > 1) s2 = search_left(rv, ts - 1, k, use_tvr);                      /* :1145-1149 */
             else s2 = ts;
-            if (e2 < s2 - 1) { err = true; break; }                                        /* IRanges() would stop */
-            out[t].start = s2; out[t].end = e2;
-            out[t].density = density_of(rv, w, t, s2, e2, lane);                           /* :1840-1844 */
-            const int wd = e2 - s2 + 1;
-            if (wd > max_width) max_width = wd;
-        }
-        /* ---- this warp's track is done; the warp that completes the read's last track writes the record head:
-         *      keep iff max interval width >= 30 over the tracks (:1847, :1857) */
-        if (lane == 0) {
-            res->track[t_only] = out[t_only];
-            /* state = {tracks done, width or -1 (error) of track 0, 1, 2}: own slot, fence, one atomic; the warp
-             * that arrives last reads the other slots past L1 */
-            *reinterpret_cast<volatile int *>(&state[1 + t_only]) = err ? -1 : max_width;
-            __threadfence();
-            if (atomicAdd(&state[0], 1) == T - 1) {
-                int any_err = 0, mw = 0;
-                for (int t = 0; t < T; t++) {
-                    const int wdt = __ldcg(&state[1 + t]);
-                    if (wdt < 0) any_err = 1; else if (wdt > mw) mw = wdt;
-                }
-                if (any_err) status |= NTL_READ_REF_ERROR;
-                else if (mw >= 30) status |= NTL_READ_KEEP;
-                res->status = status;
-                res->n_win = n_win > 0 ? n_win : 0;
-                res->win_offset = a.cnt_off[r];
-                for (int t = T; t < 3; t++) res->track[t] = out[t];
+            if (e2 < s2 - 1) err = true;                                               /* IRanges() would stop */
+            else {
+                out.start = s2; out.end = e2;
+                out.density = density_of(rv, w, t, s2, e2);                            /* :1840-1844 */
+                width = e2 - s2 + 1;
             }
         }
+    }
+    /* ---- this track is done; the thread that completes the read's last track writes the record head:
+     *      keep iff max interval width >= 30 over the tracks (:1847, :1857) */
+    res->track[t] = out;
+    /* state = {tracks done, width or -1 (error) of track 0, 1, 2}: own slot, fence, one atomic; the thread that
+     * arrives last reads the other slots past L1 */
+    *reinterpret_cast<volatile int *>(&state[1 + t]) = err ? -1 : width;
+    __threadfence();
+    if (atomicAdd(&state[0], 1) == T - 1) {
+        int any_err = 0, mw = 0;
+        for (int tt = 0; tt < T; tt++) {
+            const int wdt = __ldcg(&state[1 + tt]);
+            if (wdt < 0) any_err = 1; else if (wdt > mw) mw = wdt;
+        }
+        if (any_err) status |= NTL_READ_REF_ERROR;
+        else if (mw >= 30) status |= NTL_READ_KEEP;
+        res->status = status;
+        res->n_win = n_win > 0 ? n_win : 0;
+        res->win_offset = a.cnt_off[r];
+        ntl_track zero;
+        zero.start = 0; zero.end = 0; zero.density = 0.0;
+        for (int tt = T; tt < 3; tt++) res->track[tt] = zero;
+    }
+}
+
+__global__ void __launch_bounds__(64) ntl_locate_kernel(const ntl_read_args a)
+{
+    /* work item = (candidate read, track): the tracks of a read are independent until the keep rule;
+     * cand_state[c] = {tracks done, width (or -1: error) of track 0, 1, 2} joins them.  Candidates that the filter
+     * dropped never get here (the triage kernel writes their record). */
+    const int T = c_prm.n_tracks;
+    const int n_items = (int)a.counters[0] * T;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+        const int c = i / T;
+        locate_item(a, a.cand[c], i - c * T, a.cand_state + 4 * (size_t)c);
     }
 }
 
@@ -1127,7 +1099,10 @@ extern "C" cudaError_t ntl_k_triage(const ntl_read_args *a, cudaStream_t st)
 extern "C" cudaError_t ntl_k_locate(const ntl_read_args *a, int grid, cudaStream_t st)
 {
     if (a->n_reads <= 0) return cudaSuccess;
-    ntl_locate_kernel<<<grid, 128, 0, st>>>(*a);
+    /* one thread per (candidate, track); the number of candidates is only known on the device: enough small CTAs for
+     * every read to be one (those beyond the candidate list leave at once), spread over all SMs */
+    const long long want = ((long long)a->n_reads * 3 + 63) / 64;
+    ntl_locate_kernel<<<(int)(want < grid ? want : grid), 64, 0, st>>>(*a);
     return cudaGetLastError();
 }
 
@@ -1158,5 +1133,5 @@ extern "C" cudaError_t ntl_k_gather_windows(const ntl_read_args *a, const int64_
 
 extern "C" cudaError_t ntl_k_locate_occupancy(int *blocks_per_sm)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ntl_locate_kernel, 128, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ntl_locate_kernel, 64, 0);
 }
