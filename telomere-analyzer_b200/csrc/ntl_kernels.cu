@@ -480,44 +480,46 @@ __device__ __noinline__ void find_right_telo(const WinTab &w, int *ps, int *pe)
     *ps = start; *pe = end;
 }
 
-/* Coverage of track t (0 exact, 1 one mismatch, 2 one mismatch + TVR; the union of the trimmed hit intervals of
- * get_density_iranges, NanoTel.R:308-397) for virtual words w0 .. w0 + nw - 1 (bit b of word w = position 32 w + b),
- * recomputed from the packed read by ONE thread: the hit starts of every pattern in (previous word, word) dilated by
- * the pattern length.  hs (optional): exact hit starts of main pattern 0 for words w0 - 1 .. w0 + nw - 1 (nw + 1
- * entries: the raw hit list of NanoTel.R:349-354). */
-#define NTL_COV_MAXW 8
-__device__ __noinline__ void cov_words(const ReadView &rv, int t, int w0, int nw, u32 *cov, u32 *hs)
+/* A TEAM of eight lanes works on one (candidate, track) item: the scalar state machines run on all eight lanes alike,
+ * and where coverage has to be recomputed from the read every lane takes one word.
+ * team_cov: coverage of track t (0 exact, 1 one mismatch, 2 one mismatch + TVR; the union of the trimmed hit intervals
+ * of get_density_iranges, NanoTel.R:308-397) for virtual words w0 - 1 + sub (bit b of word w = position 32 w + b), one
+ * word per lane: hit starts of every pattern in (previous word, word) dilated by the pattern length.  Lane 0 lacks the
+ * hits of the word before its own: its word (w0 - 1) is only the look-behind; words w0 .. w0 + 6 are complete.
+ * *hs = exact hit starts of main pattern 0 in the lane's word (the raw hit list of NanoTel.R:349-354). */
+#define NTL_TEAM 8
+__device__ __noinline__ u32 team_cov(const ReadView &rv, int t, int w0, int sub, u32 tmask, u32 *hs)
 {
-    u32 prevH[2 * NTL_DEV_MAX_PAT];
-    u32 pc[4], pn[4];
-    const int np_main = c_prm.n_main, np_tvr = t == 2 ? c_prm.n_tvr : 0;
-    /* hits of word w0 - 1 first */
-    word_planes(rv, w0 - 1, pc);
-    word_planes(rv, w0, pn);
-    for (int p = 0; p < np_main + np_tvr; p++) {
-        const ntl_dev_pat &pt = p < np_main ? c_prm.main_pat[p] : c_prm.tvr_pat[p - np_main];
+    const int w = w0 - 1 + sub;
+    u32 pw[4], pn[4];
+    word_planes(rv, w, pw);
+    word_planes(rv, w + 1, pn);
+    u32 cov = 0u, h0 = 0u;
+#pragma unroll 1
+    for (int p = 0; p < c_prm.n_main; p++) {
         u32 ex, le;
-        word_hits(pt, pc, pn, &ex, &le);
-        prevH[p] = (p < np_main && t >= 1) ? le : ex;
-        if (p == 0 && hs) hs[0] = ex;
+        word_hits(c_prm.main_pat[p], pw, pn, &ex, &le);
+        if (p == 0) h0 = ex;
+        const u32 H = t >= 1 ? le : ex;
+        u32 Hp = __shfl_up_sync(tmask, H, 1, NTL_TEAM);
+        if (sub == 0) Hp = 0u;
+#pragma unroll 1
+        for (int j = 0; j < c_prm.main_pat[p].m; j++) cov |= __funnelshift_l(Hp, H, j);
     }
-    for (int i = 0; i < nw; i++) {
-        const int w = w0 + i;
-#pragma unroll
-        for (int k = 0; k < 4; k++) pc[k] = pn[k];
-        word_planes(rv, w + 1, pn);
-        u32 c = 0u;
-        for (int p = 0; p < np_main + np_tvr; p++) {
-            const ntl_dev_pat &pt = p < np_main ? c_prm.main_pat[p] : c_prm.tvr_pat[p - np_main];
+    if (t == 2) {
+#pragma unroll 1
+        for (int p = 0; p < c_prm.n_tvr; p++) {
             u32 ex, le;
-            word_hits(pt, pc, pn, &ex, &le);
-            const u32 H = (p < np_main && t >= 1) ? le : ex, Hp = prevH[p];
-            if (p == 0 && hs) hs[i + 1] = ex;
-            for (int j = 0; j < pt.m; j++) c |= __funnelshift_l(Hp, H, j);
-            prevH[p] = H;
+            word_hits(c_prm.tvr_pat[p], pw, pn, &ex, &le);
+            u32 Hp = __shfl_up_sync(tmask, ex, 1, NTL_TEAM);
+            if (sub == 0) Hp = 0u;
+#pragma unroll 1
+            for (int j = 0; j < c_prm.tvr_pat[p].m; j++) cov |= __funnelshift_l(Hp, ex, j);
         }
-        cov[i] = (w < 0 || w >= rv.n_words) ? 0u : (c & ntl_valid_word(w << 5, rv.L));     /* trim() to [1, L] */
     }
+    *hs = h0;
+    if (w < 0 || w >= rv.n_words) return 0u;
+    return cov & ntl_valid_word(w << 5, rv.L);          /* trim() to [1, L] */
 }
 
 /* bits of virtual word w that lie inside positions [lo, hi] */
@@ -528,23 +530,61 @@ __device__ __forceinline__ u32 word_range_mask(int w, int lo, int hi)
     int hb = hi - p0; if (hb > 31) hb = 31;
     return hb < lb ? 0u : ((NTL_FULL >> (31 - hb)) & (NTL_FULL << lb));
 }
+__device__ __forceinline__ int team_sum(int v, u32 tmask)
+{
+    v += __shfl_xor_sync(tmask, v, 1, NTL_TEAM);
+    v += __shfl_xor_sync(tmask, v, 2, NTL_TEAM);
+    v += __shfl_xor_sync(tmask, v, 4, NTL_TEAM);
+    return v;
+}
+__device__ __forceinline__ int team_max(int v, u32 tmask)
+{
+    v = max(v, __shfl_xor_sync(tmask, v, 1, NTL_TEAM));
+    v = max(v, __shfl_xor_sync(tmask, v, 2, NTL_TEAM));
+    v = max(v, __shfl_xor_sync(tmask, v, 4, NTL_TEAM));
+    return v;
+}
+__device__ __forceinline__ int team_min(int v, u32 tmask)
+{
+    v = min(v, __shfl_xor_sync(tmask, v, 1, NTL_TEAM));
+    v = min(v, __shfl_xor_sync(tmask, v, 2, NTL_TEAM));
+    v = min(v, __shfl_xor_sync(tmask, v, 4, NTL_TEAM));
+    return v;
+}
+/* bits of the lanes' words (lane sub holds word w0 - 1 + sub; lane 0 is never used) inside [lo, hi]: largest /
+ * smallest position, number of set bits */
+__device__ __forceinline__ int team_bits_max(u32 bits, int w0, int sub, u32 tmask, int lo, int hi)
+{
+    const u32 m = sub == 0 ? 0u : bits & word_range_mask(w0 - 1 + sub, lo, hi);
+    const int r = team_max(m ? ((w0 - 1 + sub) << 5) + 31 - __clz((int)m) : -NTL_IMAX, tmask);
+    return r == -NTL_IMAX ? NTL_NONE : r;
+}
+__device__ __forceinline__ int team_bits_min(u32 bits, int w0, int sub, u32 tmask, int lo, int hi)
+{
+    const u32 m = sub == 0 ? 0u : bits & word_range_mask(w0 - 1 + sub, lo, hi);
+    const int r = team_min(m ? ((w0 - 1 + sub) << 5) + __ffs((int)m) - 1 : NTL_IMAX, tmask);
+    return r == NTL_IMAX ? NTL_NONE : r;
+}
+__device__ __forceinline__ int team_bits_popc(u32 bits, int w0, int sub, u32 tmask, int lo, int hi)
+{
+    return team_sum(sub == 0 ? 0 : __popc(bits & word_range_mask(w0 - 1 + sub, lo, hi)), tmask);
+}
 
-/* covered positions of track t inside [lo, hi] (1 <= lo <= hi <= L), recomputed from the read */
-__device__ __noinline__ int local_count(const ReadView &rv, int t, int lo, int hi)
+/* covered positions of track t inside [lo, hi] (1 <= lo <= hi <= L), recomputed from the read, 7 words per step */
+__device__ __noinline__ int local_count(const ReadView &rv, int t, int lo, int hi, int sub, u32 tmask)
 {
     int total = 0;
-    for (int w0 = lo >> 5; w0 <= (hi >> 5); w0 += NTL_COV_MAXW) {
-        u32 cov[NTL_COV_MAXW];
-        const int nw = (hi >> 5) - w0 + 1 < NTL_COV_MAXW ? (hi >> 5) - w0 + 1 : NTL_COV_MAXW;
-        cov_words(rv, t, w0, nw, cov, nullptr);
-        for (int i = 0; i < nw; i++) total += __popc(cov[i] & word_range_mask(w0 + i, lo, hi));
+    for (int w0 = lo >> 5; w0 <= (hi >> 5); w0 += NTL_TEAM - 1) {
+        u32 hs;
+        const u32 cov = team_cov(rv, t, w0, sub, tmask, &hs);
+        total += team_bits_popc(cov, w0, sub, tmask, lo, hi);
     }
     return total;
 }
 
 /* covered bases of track t inside [a, b] (get_sub_density's numerator, NanoTel.R:467): whole blocks come from K2's
  * counts, the partial blocks at the two ends are recomputed from the read. */
-__device__ __noinline__ int covered_in(const ReadView &rv, const WinTab &w, int t, int a, int b)
+__device__ __noinline__ int covered_in(const ReadView &rv, const WinTab &w, int t, int a, int b, int sub, u32 tmask)
 {
     const int lo = a < 1 ? 1 : a, hi = b > rv.L ? rv.L : b;
     if (hi < lo) return 0;
@@ -554,98 +594,75 @@ __device__ __noinline__ int covered_in(const ReadView &rv, const WinTab &w, int 
     const int blo_s = blo * SG + 1, bhi_e = (bhi + 1) * SG < rv.L ? (bhi + 1) * SG : rv.L;
     if (blo == bhi) {
         if (lo == blo_s && hi == bhi_e) return (int)w.cnt[blo];
-        return local_count(rv, t, lo, hi);
+        return local_count(rv, t, lo, hi, sub, tmask);
     }
     int total = 0, bf = blo, bl = bhi;
-    if (lo != blo_s) { total += local_count(rv, t, lo, (blo + 1) * SG); bf = blo + 1; }
-    if (hi != bhi_e) { total += local_count(rv, t, bhi * SG + 1, hi); bl = bhi - 1; }
+    if (lo != blo_s) { total += local_count(rv, t, lo, (blo + 1) * SG, sub, tmask); bf = blo + 1; }
+    if (hi != bhi_e) { total += local_count(rv, t, bhi * SG + 1, hi, sub, tmask); bl = bhi - 1; }
     for (int j = bf; j <= bl; j++) total += (int)w.cnt[j];
     return total;
 }
 
-__device__ __forceinline__ double density_of(const ReadView &rv, const WinTab &w, int t, int a, int b)
+__device__ __forceinline__ double density_of(const ReadView &rv, const WinTab &w, int t, int a, int b, int sub, u32 tmask)
 {
-    const int cv = covered_in(rv, w, t, a, b);
+    const int cv = covered_in(rv, w, t, a, b, sub, tmask);
     return cv == 0 ? 0.0 : k3_div((double)cv, (double)(b - a + 1));      /* 0 / width is +0.0 exactly */
-}
-
-/* largest / smallest position of a set bit of bits[0 .. nw) (virtual words w0 ..) inside [lo, hi]; NTL_NONE if none */
-__device__ __forceinline__ int bits_max_in(const u32 *bits, int w0, int nw, int lo, int hi)
-{
-    for (int i = nw - 1; i >= 0; i--) {
-        const u32 m = bits[i] & word_range_mask(w0 + i, lo, hi);
-        if (m) return ((w0 + i) << 5) + 31 - __clz((int)m);
-    }
-    return NTL_NONE;
-}
-__device__ __forceinline__ int bits_min_in(const u32 *bits, int w0, int nw, int lo, int hi)
-{
-    for (int i = 0; i < nw; i++) {
-        const u32 m = bits[i] & word_range_mask(w0 + i, lo, hi);
-        if (m) return ((w0 + i) << 5) + __ffs((int)m) - 1;
-    }
-    return NTL_NONE;
 }
 
 /* get_accurate_end (NanoTel.R:1692-1721).  `ranges` are the raw exact hits of the single fixed pattern on track A
  * (NanoTel.R:349-354) and the reduced runs of the coverage otherwise (:341-345). */
-__device__ __noinline__ int get_accurate_end(const ReadView &rv, int t, int telo_end)
+__device__ __noinline__ int get_accurate_end(const ReadView &rv, int t, int telo_end, int sub, u32 tmask)
 {
     if (telo_end == -1) return -1;
-    /* range ends inside [e - 99, e + 50]: coverage of the words holding [e - 99, e + 51] */
+    /* range ends inside [e - 99, e + 50]: the words holding [e - 99, e + 51] (at most 6) are lanes 1 .. 7 */
     const int w0 = (telo_end - 99) >> 5;
-    const int nw = ((telo_end + 51) >> 5) - w0 + 1;                      /* <= 6 */
-    u32 cov[NTL_COV_MAXW], hs[NTL_COV_MAXW + 1], en[NTL_COV_MAXW];
-    cov_words(rv, t, w0, nw, cov, hs);
+    u32 hs;
+    const u32 cov = team_cov(rv, t, w0, sub, tmask, &hs);
+    u32 en;
     if (t == 0 && c_prm.raw_hits_A) {
-        const int m = c_prm.main_pat[0].m;
-        for (int i = 0; i < nw; i++) en[i] = __funnelshift_l(hs[i], hs[i + 1], m - 1);      /* end = start + m - 1 */
+        const u32 hp = __shfl_up_sync(tmask, hs, 1, NTL_TEAM);
+        en = __funnelshift_l(hp, hs, c_prm.main_pat[0].m - 1);           /* end = start + m - 1 */
     } else {
-        for (int i = 0; i < nw; i++) {
-            const u32 nx = i + 1 < nw ? cov[i + 1] : 0u;                 /* the last word is only the look-ahead */
-            en[i] = cov[i] & ~((cov[i] >> 1) | (nx << 31));
-        }
+        u32 nx = __shfl_down_sync(tmask, cov, 1, NTL_TEAM);
+        if (sub == NTL_TEAM - 1) nx = 0u;                                /* lane 7's word is beyond e + 51: only a look-ahead */
+        en = cov & ~((cov >> 1) | (nx << 31));
     }
     int e_index = telo_end;
-    const int m1 = bits_max_in(en, w0, nw, telo_end - 99, telo_end);
+    const int m1 = team_bits_max(en, w0, sub, tmask, telo_end - 99, telo_end);
     if (m1 != NTL_NONE) e_index = m1;
-    const int m2 = bits_max_in(en, w0, nw, telo_end + 1, telo_end + 50);
+    const int m2 = team_bits_max(en, w0, sub, tmask, telo_end + 1, telo_end + 50);
     if (m2 != NTL_NONE) e_index = m2;
     return e_index;
 }
 
 /* get_accurate_start (NanoTel.R:1726-1764) */
-__device__ __noinline__ int get_accurate_start(const ReadView &rv, int t, int telo_start)
+__device__ __noinline__ int get_accurate_start(const ReadView &rv, int t, int telo_start, int sub, u32 tmask)
 {
     if (telo_start == -1) return telo_start;
     const int s = telo_start;
-    /* range starts inside [s - 36, s + 99]: coverage of the words holding [s - 37, s + 99] */
+    /* range starts inside [s - 36, s + 99]: the words holding [s - 37, s + 99] (at most 6) are lanes 1 .. 7 */
     const int w0 = (s - 37) >> 5;
-    const int nw = ((s + 99) >> 5) - w0 + 1;                             /* <= 6 */
-    u32 cov[NTL_COV_MAXW], hs[NTL_COV_MAXW + 1], st[NTL_COV_MAXW];
-    cov_words(rv, t, w0, nw, cov, hs);
-    if (t == 0 && c_prm.raw_hits_A) {
-        for (int i = 0; i < nw; i++) st[i] = hs[i + 1];
-    } else {
-        for (int i = 0; i < nw; i++) {
-            const u32 pv = i > 0 ? cov[i - 1] : 0u;                      /* the first word is only the look-behind */
-            st[i] = cov[i] & ~((cov[i] << 1) | (pv >> 31));
-        }
+    u32 hs;
+    const u32 cov = team_cov(rv, t, w0, sub, tmask, &hs);
+    u32 st;
+    if (t == 0 && c_prm.raw_hits_A) st = hs;
+    else {
+        const u32 pv = __shfl_up_sync(tmask, cov, 1, NTL_TEAM);          /* lane 1 looks behind into lane 0's (incomplete) word:
+                                                                            only bit 32 w0 could be wrong, and it is < s - 36 */
+        st = cov & ~((cov << 1) | (pv >> 31));
     }
-    int c50 = 0;
-    for (int i = 0; i < nw; i++) c50 += __popc(cov[i] & word_range_mask(w0 + i, s, s + 49));
+    const int c50 = team_bits_popc(cov, w0, sub, tmask, s, s + 49);
     const double first_50 = k3_div((double)c50, 50.0);                         /* IRanges(start, width = 50) :1732 */
-    /* the look-behind word: range starts are only asked for at positions >= s - 36 > 32 w0 + 31 - 32 ... see below */
     if (first_50 < 0.3) {
-        const int a = bits_min_in(st, w0, nw, s + 48, s + 99);
+        const int a = team_bits_min(st, w0, sub, tmask, s + 48, s + 99);
         if (a != NTL_NONE) telo_start = a;
-        const int b = bits_min_in(st, w0, nw, s + 33, s + 48);
+        const int b = team_bits_min(st, w0, sub, tmask, s + 33, s + 48);
         if (b != NTL_NONE) telo_start = b;
     } else {
-        const int a = bits_min_in(st, w0, nw, s, s + 99);
+        const int a = team_bits_min(st, w0, sub, tmask, s, s + 99);
         if (a != NTL_NONE) telo_start = a;
         if (first_50 >= 0.72) {
-            const int b = bits_min_in(st, w0, nw, s - 36, s - 1);
+            const int b = team_bits_min(st, w0, sub, tmask, s - 36, s - 1);
             if (b != NTL_NONE) telo_start = b;
         }
     }
@@ -912,78 +929,96 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
  * K3b: full locator, one THREAD per (candidate read, track); the thread that completes a read's last track writes
  * the record head.
  * ============================================================================================================= */
-__device__ void locate_item(const ntl_read_args &a, int r, int t, int *state)
+/* One item per team, four teams per warp.  The four items of a warp are walked in PHASES with a warp barrier between
+ * them: inside a phase the teams run the same code (the coverage recomputation has fixed trip counts), and teams that
+ * diverged in a data-dependent phase (the window scans) meet again at the next barrier instead of executing the rest
+ * of their items one after the other.  valid = false: a team without an item (it only keeps the barriers company). */
+__device__ void locate_items(const ntl_read_args &a, bool valid, int r, int t, int *state, int sub, u32 tmask)
 {
-    ntl_read_result *res = reinterpret_cast<ntl_read_result *>(a.results) + r;
-    ntl_stage *stg = a.stages ? reinterpret_cast<ntl_stage *>(a.stages) + (size_t)r * 3 : nullptr;
-
     ReadView rv;
-    rv_init(rv, a, r);
+    WinTab w;
+    rv.L = 0; rv.fmt = 0; rv.base = nullptr; rv.n_words = 0; rv.n_raw = 0; rv.ccov = nullptr; rv.cwb = nullptr;
+    w.cnt = nullptr; w.n = 0; w.nb = 0; w.Q = 1; w.SG = 1; w.S = 1; w.L = 0; w.thr_reg = 0; w.thr_last = 0;
     const int S = c_prm.S, T = c_prm.n_tracks;
-    const int n_win = ntl_nwin(rv.L, S);
-    int status = rv.fmt ? NTL_READ_IUPAC : 0;
-    if (n_win <= 0) status |= NTL_READ_NO_WINDOWS;
-
+    int n_win = 0, status = 0;
     ntl_track out;
     out.start = 0; out.end = 0; out.density = 0.0;
     bool err = false;
-    int width = 0;
-    {
-        WinTab w;
+    int width = 0, ts = -1, te = -1, cs = -1, ce = -1, as = -1, ae = -1, s2 = 0, e2 = 0;
+    double acc_density = 0.0;
+    const int k = t >= 1 ? 1 : 0;
+    const bool use_tvr = t == 2;
+    ntl_stage *stg = nullptr;
+
+    /* ---- phase 0: tables, coarse interval (window scans: data dependent) */
+    if (valid) {
+        stg = a.stages ? reinterpret_cast<ntl_stage *>(a.stages) + (size_t)r * 3 : nullptr;
+        rv_init(rv, a, r);
+        n_win = ntl_nwin(rv.L, S);
+        status = rv.fmt ? NTL_READ_IUPAC : 0;
+        if (n_win <= 0) status |= NTL_READ_NO_WINDOWS;
         w.cnt = a.cnt[t] + a.cnt_off[r]; w.n = n_win > 0 ? n_win : 0; w.S = S; w.L = rv.L;
         w.Q = c_prm.Q; w.SG = c_prm.SG; w.nb = (rv.L + c_prm.SG - 1) / c_prm.SG;
         w.thr_reg = c_prm.thr_reg;
         w.thr_last = w.n > 0 ? (int)a.thr[wt_end(w, w.n - 1) - wt_start(w, w.n - 1) + 1] : 0;
-        const int k = t >= 1 ? 1 : 0;
-        const bool use_tvr = t == 2;
-
-        int ts, te;
         find_telo_position(w, 3.0, 2.0, &ts, &te);                                     /* :1084-1086 */
-        const double telo_density = density_of(rv, w, t, ts, te);                      /* :1099 */
+        /* the coarse interval is made of whole windows: its density needs no coverage recomputation */
+        const double telo_density = density_of(rv, w, t, ts, te, sub, tmask);          /* :1099 */
         const int num_rows = (te - ts + 1) / S;                                        /* :1103 */
         if (telo_density < 0.85 && num_rows > 5) {                                     /* :1104-1110 */
             const double min_rows = num_rows <= 7 ? (double)(num_rows - 2) : 7.0;
             const double min_score = 0.6 * min_rows;
             find_telo_position(w, min_rows, min_score, &ts, &te);
         }
-        const int cs = ts, ce = te;
-        int start_acc = get_accurate_start(rv, t, ts);                                 /* :1119 */
-        int end_acc = get_accurate_end(rv, t, te);                                     /* :1120 */
+        cs = ts; ce = te;
+    }
+    __syncwarp();
+    /* ---- phase 1, 2: accurate start / end (one coverage block each) */
+    int start_acc = -1, end_acc = -1;
+    if (valid) start_acc = get_accurate_start(rv, t, ts, sub, tmask);                  /* :1119 */
+    __syncwarp();
+    if (valid) end_acc = get_accurate_end(rv, t, te, sub, tmask);                      /* :1120 */
+    __syncwarp();
+    if (valid) {
         if (start_acc > end_acc) end_acc = start_acc;                                  /* :1122-1124 */
         ts = start_acc; te = end_acc;
-        const int as = ts, ae = te;
-        double acc_density = 0.0;
-        if (stg) acc_density = density_of(rv, w, t, ts, te);
+        as = ts; ae = te;
+        if (stg) acc_density = density_of(rv, w, t, ts, te, sub, tmask);
         if (te - ts + 1 < 100) {                                                       /* :1129-1136 */
             if (c_prm.right_edge) {
                 if (w.n == 0) err = true;                                              /* R stops at :859-861 */
                 else find_right_telo(w, &ts, &te);
             } else find_left_telo(w, &ts, &te);
         }
-        if (!err) {
-            if (stg) {
-                ntl_stage sg;
-                sg.coarse_start = cs; sg.coarse_end = ce; sg.acc_start = as; sg.acc_end = ae;
-                sg.edge_start = ts; sg.edge_end = te; sg.acc_density = acc_density;
-                stg[t] = sg;
-            }
-            int e2, s2;
-            if (te < rv.L) e2 = search_right(rv, te + 1, k, use_tvr);                  /* :1140-1144 */
-            else e2 = te;
-            if (ts > 1) s2 = search_left(rv, ts - 1, k, use_tvr);                      /* :1145-1149 */
-            else s2 = ts;
-            if (e2 < s2 - 1) err = true;                                               /* IRanges() would stop */
-            else {
-                out.start = s2; out.end = e2;
-                out.density = density_of(rv, w, t, s2, e2);                            /* :1840-1844 */
-                width = e2 - s2 + 1;
-            }
+        if (!err && stg && sub == 0) {
+            ntl_stage sg;
+            sg.coarse_start = cs; sg.coarse_end = ce; sg.acc_start = as; sg.acc_end = ae;
+            sg.edge_start = ts; sg.edge_end = te; sg.acc_density = acc_density;
+            stg[t] = sg;
         }
     }
-    /* ---- this track is done; the thread that completes the read's last track writes the record head:
+    __syncwarp();
+    /* ---- phase 3, 4: the 18-bp re-match searches */
+    if (valid && !err) e2 = te < rv.L ? search_right(rv, te + 1, k, use_tvr) : te;      /* :1140-1144 */
+    __syncwarp();
+    if (valid && !err) s2 = ts > 1 ? search_left(rv, ts - 1, k, use_tvr) : ts;          /* :1145-1149 */
+    __syncwarp();
+    /* ---- phase 5: final density (:1840-1844) */
+    if (valid && !err) {
+        if (e2 < s2 - 1) err = true;                                                   /* IRanges() would stop */
+        else {
+            out.start = s2; out.end = e2;
+            out.density = density_of(rv, w, t, s2, e2, sub, tmask);
+            width = e2 - s2 + 1;
+        }
+    }
+    __syncwarp();
+    /* ---- this track is done; the team that completes the read's last track writes the record head:
      *      keep iff max interval width >= 30 over the tracks (:1847, :1857) */
+    if (!valid || sub != 0) return;
+    ntl_read_result *res = reinterpret_cast<ntl_read_result *>(a.results) + r;
     res->track[t] = out;
-    /* state = {tracks done, width or -1 (error) of track 0, 1, 2}: own slot, fence, one atomic; the thread that
+    /* state = {tracks done, width or -1 (error) of track 0, 1, 2}: own slot, fence, one atomic; the team that
      * arrives last reads the other slots past L1 */
     *reinterpret_cast<volatile int *>(&state[1 + t]) = err ? -1 : width;
     __threadfence();
@@ -1007,13 +1042,18 @@ __device__ void locate_item(const ntl_read_args &a, int r, int t, int *state)
 __global__ void __launch_bounds__(64) ntl_locate_kernel(const ntl_read_args a)
 {
     /* work item = (candidate read, track): the tracks of a read are independent until the keep rule;
-     * cand_state[c] = {tracks done, width (or -1: error) of track 0, 1, 2} joins them.  Candidates that the filter
+     * cand_state[c] = {tracks done, width (or -1: error) of track 0, 1, 2} joins them.  Reads that the filter
      * dropped never get here (the triage kernel writes their record). */
     const int T = c_prm.n_tracks;
     const int n_items = (int)a.counters[0] * T;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
-        const int c = i / T;
-        locate_item(a, a.cand[c], i - c * T, a.cand_state + 4 * (size_t)c);
+    const int lane = threadIdx.x & 31, sub = lane & (NTL_TEAM - 1);
+    const u32 tmask = 0xffu << (lane & 24);
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp * 4; base < n_items; base += n_warps * 4) {     /* warp-uniform: every team keeps the barriers */
+        const int i = base + (lane >> 3);
+        const bool valid = i < n_items;
+        const int c = valid ? i / T : 0;
+        locate_items(a, valid, valid ? a.cand[c] : 0, valid ? i - c * T : 0, a.cand_state + 4 * (size_t)c, sub, tmask);
     }
 }
 
@@ -1101,7 +1141,7 @@ extern "C" cudaError_t ntl_k_locate(const ntl_read_args *a, int grid, cudaStream
     if (a->n_reads <= 0) return cudaSuccess;
     /* one thread per (candidate, track); the number of candidates is only known on the device: enough small CTAs for
      * every read to be one (those beyond the candidate list leave at once), spread over all SMs */
-    const long long want = ((long long)a->n_reads * 3 + 63) / 64;
+    const long long want = ((long long)a->n_reads * 3 * 8 + 63) / 64;        /* eight lanes per item */
     ntl_locate_kernel<<<(int)(want < grid ? want : grid), 64, 0, st>>>(*a);
     return cudaGetLastError();
 }
