@@ -37,6 +37,7 @@ cudaError_t ntl_k_filter(const ntl_read_args *a, cudaStream_t st);
 cudaError_t ntl_k_items(const uint8_t *active, int n_items, int32_t *items, uint32_t *counter, cudaStream_t st);
 cudaError_t ntl_k_triage(const ntl_read_args *a, cudaStream_t st);
 cudaError_t ntl_k_locate(const ntl_read_args *a, int grid, cudaStream_t st);
+cudaError_t ntl_k_cls(const ntl_read_args *a, long long n_bytes, int T, uint32_t blk_thr, cudaStream_t st);
 cudaError_t ntl_k_locate_occupancy(int *blocks_per_sm);
 cudaError_t ntl_k_gather_windows(const ntl_read_args *a, const int64_t *list, int n_list, uint16_t *dst, int T, cudaStream_t st);
 }
@@ -110,7 +111,7 @@ int gcd_i(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } retur
  * with a large odd part, S < 16): the generic scan kernel handles the batch, blocks = windows. */
 void choose_geometry(int S, ntl_dev_params *d)
 {
-    d->SG = S; d->Q = 1; d->W = 2; d->BPS = 0;
+    d->SG = S; d->Q = 1; d->W = 2; d->BPS = 0; d->cls_bps = 8;
     for (int q = 1; q <= 64; q++) {
         if (S % q) continue;
         const int sg = S / q;
@@ -126,11 +127,12 @@ void choose_geometry(int S, ntl_dev_params *d)
         }
         if (32 * best_w / sg > 64) continue;
         d->SG = sg; d->Q = q; d->W = best_w; d->BPS = 32 * best_w / sg;
+        d->cls_bps = d->BPS <= 8 ? d->BPS : 8;              /* class bits: one byte per span, else dense (ntl_dev.h) */
         return;
     }
 }
 
-void generic_geometry(ntl_dev_params *d) { d->SG = d->S; d->Q = 1; d->W = 2; d->BPS = 0; }
+void generic_geometry(ntl_dev_params *d) { d->SG = d->S; d->Q = 1; d->W = 2; d->BPS = 0; d->cls_bps = 8; }
 
 } // namespace
 
@@ -159,7 +161,7 @@ struct ntl_dev_ctx {
     size_t arena4_off = 0;                  /* byte offset of the 4-bit arena (its lead included) inside the packed buffers */
 
     PinnedBuf h_packed, h_meta, h_results, h_cnt, h_stages, h_list;
-    DevBuf d_packed, d_meta, d_results, d_cnt, d_stages, d_pass, d_counter, d_thr, d_flags, d_kept, d_list, d_items;
+    DevBuf d_packed, d_meta, d_results, d_cnt, d_cls, d_stages, d_pass, d_counter, d_thr, d_flags, d_kept, d_list, d_items;
     std::vector<int64_t> kept_off;          /* per read: first element of its rows in h_cnt, -1 = not downloaded */
     std::vector<uint16_t> win_scratch;      /* ntl_get_windows of a read that was not kept: fetched on demand     */
     ntl_timings tm;
@@ -291,7 +293,7 @@ void dev_destroy(ntl_dev_ctx *c)
     if (c->jit) ntl_jit_free(c->jit);
     c->h_packed.release(); c->h_meta.release(); c->h_results.release(); c->h_cnt.release(); c->h_stages.release();
     c->h_list.release(); c->d_kept.release(); c->d_list.release(); c->d_items.release();
-    c->d_packed.release(); c->d_meta.release(); c->d_results.release(); c->d_cnt.release(); c->d_stages.release();
+    c->d_packed.release(); c->d_meta.release(); c->d_results.release(); c->d_cnt.release(); c->d_cls.release(); c->d_stages.release();
     c->d_pass.release(); c->d_counter.release(); c->d_thr.release(); c->d_flags.release();
     for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int k = 0; k < NTL_EVENT_RING; k++)
@@ -403,6 +405,13 @@ int dev_create(ntl_dev_ctx **out, const ntl_params *p, int device, int host_thre
 inline int64_t spans_of(int64_t L, int W) { return (L + 32 * (int64_t)W - 1) / (32 * (int64_t)W); }
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+/* bytes of one track's class-bit plane (ntl_dev.h), a multiple of 16 */
+size_t cls_plane_bytes(const ntl_dev_ctx *c)
+{
+    return (((size_t)c->total_blocks + c->dev.cls_bps - 1) / c->dev.cls_bps + 15 + 16) & ~(size_t)15;
+}
+inline uint32_t blk_thr_of(const ntl_dev_ctx *c) { return (uint32_t)((c->dev.thr_reg + c->dev.Q - 1) / c->dev.Q); }
+
 int ensure_device_buffers(ntl_dev_ctx *c)
 {
     const int32_t n = c->n_reads;
@@ -412,6 +421,7 @@ int ensure_device_buffers(ntl_dev_ctx *c)
     CK(c, c->d_meta.ensure(c->meta_bytes + 16));
     CK(c, c->d_results.ensure((size_t)n * sizeof(ntl_read_result) + 64));
     CK(c, c->d_cnt.ensure((size_t)c->total_blocks * 2 * T + 64));
+    CK(c, c->d_cls.ensure(cls_plane_bytes(c) * T + 64));
     CK(c, c->d_pass.ensure((size_t)n + 64));
     CK(c, c->d_flags.ensure((size_t)n * 20 + 128));       /* candidate list + per-candidate join state of the locate kernel */
     const size_t n_items = (size_t)(c->spans2 + c->spans4) / NTL_ITEM_SPANS + 2;
@@ -708,6 +718,7 @@ void fill_read_args(const ntl_dev_ctx *c, ntl_read_args *out)
     ra.fmt = (const uint8_t *)(dm + c->off_fmt);
     ra.pass = c->dev.use_filter ? (uint8_t *)c->d_pass.p : nullptr;
     for (int t = 0; t < 3; t++) ra.cnt[t] = t < T ? (uint16_t *)c->d_cnt.p + (size_t)t * c->total_blocks : nullptr;
+    for (int t = 0; t < 3; t++) ra.cls[t] = t < T ? (uint8_t *)c->d_cls.p + (size_t)t * cls_plane_bytes(c) : nullptr;
     ra.results = c->d_results.p;
     ra.thr = (const uint16_t *)c->d_thr.p;
     ra.dens = (const double *)((const char *)c->d_thr.p + c->dens_offset);
@@ -772,6 +783,9 @@ int dev_enqueue(ntl_dev_ctx *c)
             sa.n_reads = n; sa.len = ra.len; sa.woff = ra.woff; sa.fmt = ra.fmt; sa.pass = ra.pass;
             sa.cnt_base = arena ? c->spans2 * c->dev.BPS : 0;
             for (int t = 0; t < 3; t++) sa.cnt[t] = ra.cnt[t];
+            for (int t = 0; t < 3; t++) sa.cls[t] = c->dev.BPS <= 8 ? ra.cls[t] : nullptr;
+            sa.cls_base = arena ? c->spans2 : 0;
+            sa.blk_thr = (int32_t)blk_thr_of(c);
             cudaError_t e = ntl_jit_launch(c->jit, &sa, arena, c->n_sms, c->stream);
             if (e != cudaSuccess) return fail(c, NTL_ERR_CUDA, "span scan kernel launch failed: %s", cudaGetErrorString(e));
             launches++;
@@ -780,6 +794,10 @@ int dev_enqueue(ntl_dev_ctx *c)
     } else if (n > 0) {
         CK(c, cudaMemsetAsync(c->d_cnt.p, 0, (size_t)c->total_blocks * 2 * T, c->stream));
         CK(c, ntl_k_scan_generic(&ra, c->generic_grid, c->stream));
+        launches++;
+    }
+    if (n > 0 && !(spans && c->jit && c->dev.BPS <= 8)) {     /* the scan kernel did not write the class bits itself */
+        CK(c, ntl_k_cls(&ra, (long long)((c->total_blocks + 7) / 8), T, blk_thr_of(c), c->stream));
         launches++;
     }
     CK(c, cudaEventRecord(ev[2], c->stream));

@@ -16,6 +16,14 @@
  *   the read).  Block j of span s lives at entry (s * blocks_per_span + j) of the track's plane, so a read's blocks
  *   are contiguous from cnt_off[r] = first_span[r] * blocks_per_span on.  A window of split_telo (NanoTel.R:199-227)
  *   is Q = subseq_length / SG consecutive blocks; the last window takes every remaining block.
+ *   CLASS BITS.  Beside the counts every track has a plane of class bits: one bit per block, set iff the block's count
+ *   reaches blk_thr = ceil(thr_reg / Q) -- for Q = 1 exactly "this (regular) window is telomeric" (NanoTel.R:751-758),
+ *   for Q > 1 a necessary condition for the window that holds the block.  The triage and locate kernels find telomeric
+ *   windows by scanning these bits (1/16 of the bytes of the counts).  Bit address of block g of the plane:
+ *       (g / cls_bps) * 8 + g % cls_bps
+ *   cls_bps = blocks per span when a span holds at most 8 blocks (the scan kernel stores ONE byte per span and
+ *   track), else 8 (dense bits, written from the counts by ntl_cls_kernel).  cnt_off[r] is a multiple of 8 and of the
+ *   blocks per span, so a read's bits start on a byte.  Bits outside a scanned read's blocks are undefined.
  */
 #ifndef NTL_DEV_H
 #define NTL_DEV_H
@@ -66,7 +74,7 @@ typedef struct {
     int32_t Q;                         /* blocks per regular window = S / SG                                      */
     int32_t W;                         /* position words per span                                                 */
     int32_t BPS;                       /* blocks per span = 32 W / SG (0: generic geometry, no spans)             */
-    int32_t pad0;
+    int32_t cls_bps;                   /* class-bit layout: blocks per byte (see above)                           */
     int32_t main_group_begin[NTL_DEV_MAX_PAT + 1];
     int32_t tvr_group_begin[NTL_DEV_MAX_PAT + 1];
     double  min_density;
@@ -90,6 +98,10 @@ typedef struct {
     const uint8_t  *pass;              /* [n_reads] edge-filter verdict, or NULL                                  */
     int64_t         cnt_base;          /* entry of span 0 of this arena inside a track's block-count plane        */
     uint16_t       *cnt[3];            /* per track: covered bases per block                                      */
+    uint8_t        *cls[3];            /* per track: class byte of every span (blocks per span <= 8), or NULL       */
+    int64_t         cls_base;          /* entry of span 0 of this arena inside a track's class plane              */
+    int32_t         blk_thr;           /* a block's class bit: count >= blk_thr                                    */
+    int32_t         pad;
 } ntl_scan_args;
 
 /* Arguments of the filter (K4), generic scan and locate (K3) kernels. */
@@ -102,6 +114,7 @@ typedef struct {
     const uint8_t  *fmt;               /* [n_reads] 0 = 2-bit, 1 = 4-bit                                          */
     uint8_t        *pass;              /* [n_reads] written by K4, read by K2/K3; NULL when the filter is off     */
     uint16_t       *cnt[3];            /* per track: covered bases per block                                      */
+    uint8_t        *cls[3];            /* per track: class bits of the blocks (layout: cls_bps)                    */
     const uint16_t *thr;               /* [2 S + 2] smallest covered count that makes a window of that width
                                           telomeric: !(count / width < min_density), NanoTel.R:751-758         */
     const double   *dens;              /* [S + 1] dens[c] = (double)c / (double)S (NanoTel.R:467 for width-S windows) */

@@ -6,7 +6,7 @@
  *   K4  ntl_filter_kernel      --use_filter edge filter            (filter_reads/filter_density, NanoTel.R:2083-2163);
  *                              also marks the spans / work items of the reads it keeps for the span scan
  *       ntl_items_kernel       compacts the marked work items into the list the span scan walks
- *   K3a ntl_triage_kernel      eight lanes per read: proves that a read has no telomeric window on any track and no
+ *   K3a ntl_triage_kernel      one thread per read: proves that a read has no telomeric window on any track and no
  *                              hit in its first 18 bases and writes its (trivial) record, or hands it to K3b
  *   K3b ntl_locate_kernel      one warp per (candidate read, track): locator and refinement (find_telo_position_wraper
  *                              NanoTel.R:1080-1155 and everything it calls, analyze_read's densities and keep rule
@@ -32,6 +32,26 @@ typedef unsigned int u32;
 #define NTL_FULL 0xffffffffu
 
 __constant__ ntl_dev_params c_prm;
+
+#ifdef NTL_K3_CLOCK
+/* development aid (build.py with NTL_EXTRA_NVCC_FLAGS=-DNTL_K3_CLOCK): cycles per phase of the locate kernel, per warp:
+ * [phase][0] sum, [1] max, [2] samples */
+__device__ unsigned long long g_k3clk[16][3];
+#define K3CLK(ph) do { __syncwarp(); const long long now_ = clock64(); if ((threadIdx.x & 31) == 0) { \
+    atomicAdd(&g_k3clk[ph][0], (unsigned long long)(now_ - clk_)); atomicMax(&g_k3clk[ph][1], (unsigned long long)(now_ - clk_)); \
+    atomicAdd(&g_k3clk[ph][2], 1ull); } clk_ = clock64(); } while (0)
+#define K3CLK_BEGIN long long clk_ = clock64()
+extern "C" int ntl_debug_k3_clock(unsigned long long *out)
+{
+    if (cudaMemcpyFromSymbol(out, g_k3clk, sizeof g_k3clk) != cudaSuccess) return -1;
+    unsigned long long z[16][3] = {};
+    cudaMemcpyToSymbol(g_k3clk, z, sizeof z);
+    return 16;
+}
+#else
+#define K3CLK(ph) do { } while (0)
+#define K3CLK_BEGIN do { } while (0)
+#endif
 
 __device__ __forceinline__ int ntl_nwin(int L, int S)
 {
@@ -314,7 +334,68 @@ struct WinTab {                 /* the window table of one track (analyze_subtel
     const uint16_t *cnt;        /* covered bases per block of SG positions (K2); window k = blocks k Q .. k Q + Q - 1, */
     int n, nb, Q, SG, S, L;     /* the last window = every remaining block (n windows, nb blocks)                     */
     int thr_reg, thr_last;      /* smallest telomeric count of a regular window / of this read's last window */
+    const u32 *cls;             /* the track's class-bit plane (ntl_dev.h) as 32-bit words                            */
+    long long bit0;             /* bit address of the read's block 0                                                  */
+    int bps;                    /* blocks per class byte                                                              */
 };
+/* bit address of block b of the read / block of a bit address */
+__device__ __forceinline__ long long wt_bit_of_block(const WinTab &w, int b)
+{
+    return w.bps == 8 ? w.bit0 + b : w.bit0 + (long long)(b / w.bps) * 8 + b % w.bps;
+}
+__device__ __forceinline__ int wt_block_of_bit(const WinTab &w, long long a)
+{
+    const int rel = (int)(a - w.bit0);
+    return w.bps == 8 ? rel : (rel >> 3) * w.bps + (rel & 7);
+}
+
+/* First / last set bit of a class plane inside the bit addresses [a_lo, a_hi] (-1: none), searched by a TEAM of eight
+ * lanes: 512 bits per step, two independent 32-bit loads per lane.  Every lane of the team returns the same value. */
+#define NTL_TEAM 8
+__device__ __forceinline__ u32 cls_word(const u32 *pl, long long wi, long long a_lo, long long a_hi)
+{
+    if (wi < (a_lo >> 5) || wi > (a_hi >> 5)) return 0u;
+    u32 v = __ldg(pl + wi);
+    if (wi == (a_lo >> 5)) v &= NTL_FULL << (int)(a_lo & 31);
+    if (wi == (a_hi >> 5)) v &= NTL_FULL >> (31 - (int)(a_hi & 31));
+    return v;
+}
+__device__ __noinline__ long long team_first_bit(const u32 *pl, long long a_lo, long long a_hi, int sub, u32 tmask, int lane)
+{
+    if (a_hi < a_lo) return -1;
+    for (long long w0 = a_lo >> 5; w0 <= (a_hi >> 5); w0 += 2 * NTL_TEAM) {
+        const u32 v0 = cls_word(pl, w0 + sub, a_lo, a_hi), v1 = cls_word(pl, w0 + NTL_TEAM + sub, a_lo, a_hi);
+        const u32 m0 = (__ballot_sync(tmask, v0 != 0u) >> (lane & 24)) & 0xffu;
+        const u32 m1 = (__ballot_sync(tmask, v1 != 0u) >> (lane & 24)) & 0xffu;
+        if (m0) {
+            const int src = __ffs((int)m0) - 1;
+            return ((w0 + src) << 5) + __ffs((int)__shfl_sync(tmask, v0, src, NTL_TEAM)) - 1;
+        }
+        if (m1) {
+            const int src = __ffs((int)m1) - 1;
+            return ((w0 + NTL_TEAM + src) << 5) + __ffs((int)__shfl_sync(tmask, v1, src, NTL_TEAM)) - 1;
+        }
+    }
+    return -1;
+}
+__device__ __noinline__ long long team_last_bit(const u32 *pl, long long a_lo, long long a_hi, int sub, u32 tmask, int lane)
+{
+    if (a_hi < a_lo) return -1;
+    for (long long w0 = a_hi >> 5; w0 >= (a_lo >> 5); w0 -= 2 * NTL_TEAM) {
+        const u32 v0 = cls_word(pl, w0 - sub, a_lo, a_hi), v1 = cls_word(pl, w0 - NTL_TEAM - sub, a_lo, a_hi);
+        const u32 m0 = (__ballot_sync(tmask, v0 != 0u) >> (lane & 24)) & 0xffu;
+        const u32 m1 = (__ballot_sync(tmask, v1 != 0u) >> (lane & 24)) & 0xffu;
+        if (m0) {
+            const int src = __ffs((int)m0) - 1;                      /* the lowest lane holds the highest word */
+            return ((w0 - src) << 5) + 31 - __clz((int)__shfl_sync(tmask, v0, src, NTL_TEAM));
+        }
+        if (m1) {
+            const int src = __ffs((int)m1) - 1;
+            return ((w0 - NTL_TEAM - src) << 5) + 31 - __clz((int)__shfl_sync(tmask, v1, src, NTL_TEAM));
+        }
+    }
+    return -1;
+}
 __device__ __forceinline__ int wt_start(const WinTab &w, int k) { return 1 + k * w.S; }
 __device__ __forceinline__ int wt_end(const WinTab &w, int k) { return k == w.n - 1 ? w.L : (k + 1) * w.S; }
 __device__ __forceinline__ int wt_count(const WinTab &w, int k)
@@ -339,78 +420,79 @@ __device__ __forceinline__ double wt_density_of_count(const WinTab &w, int k, in
 
 /* First telomeric window at or after k0 (n if none) / last telomeric window at or before k0 (-1 if none).  The
  * reference's scans walk window by window; between two telomeric windows nothing happens but resets, so the walk may
- * jump.  When a window is one block (Q == 1) the regular windows are skipped 32 at a time: four independent 16-byte
- * loads of 8 counts (a read's block range starts on a multiple of 8 entries), two compares per pair of counts. */
-__device__ __forceinline__ bool pair_has_telo(u32 x, u32 thr16) { return (x << 16) >= thr16 || x >= thr16; }
-__device__ __forceinline__ bool quad_has_telo(const uint4 &v, u32 thr16)
+ * jump: the regular windows are searched through the class bits of their blocks (exact for Q == 1; for Q > 1 a set
+ * bit names a window whose count is then checked), 512 blocks per team step; the last window (own width and
+ * threshold) is always decided from its count. */
+__device__ __noinline__ int next_telo_fwd(const WinTab &w, int k0, int sub, u32 tmask, int lane)
 {
-    return pair_has_telo(v.x, thr16) || pair_has_telo(v.y, thr16) || pair_has_telo(v.z, thr16) || pair_has_telo(v.w, thr16);
-}
-
-__device__ __noinline__ int next_telo_fwd(const WinTab &w, int k0)
-{
-    const int n = w.n;
+    const int n = w.n, nr = n - 1;                                       /* regular windows 0 .. nr - 1 */
     int k = k0 < 0 ? 0 : k0;
-    if (w.Q == 1) {
-        const int nr = n - 1;                                            /* regular windows 0 .. nr - 1 */
-        const u32 thr16 = (u32)w.thr_reg << 16;
-        while (k < nr && (k & 7)) { if ((int)w.cnt[k] >= w.thr_reg) return k; k++; }
-        const uint4 *cv = reinterpret_cast<const uint4 *>(w.cnt);
-        while (k + 32 <= nr) {
-            const uint4 v0 = __ldg(cv + (k >> 3)), v1 = __ldg(cv + (k >> 3) + 1), v2 = __ldg(cv + (k >> 3) + 2), v3 = __ldg(cv + (k >> 3) + 3);
-            if (quad_has_telo(v0, thr16) || quad_has_telo(v1, thr16) || quad_has_telo(v2, thr16) || quad_has_telo(v3, thr16)) break;
-            k += 32;
-        }
-        while (k < nr) { if ((int)w.cnt[k] >= w.thr_reg) return k; k++; }
-        if (k == nr && nr >= 0 && wt_telo_count(w, nr, wt_count(w, nr))) return nr;
-        return n;
+    while (k < nr) {
+        const long long a = team_first_bit(w.cls, wt_bit_of_block(w, k * w.Q), wt_bit_of_block(w, nr * w.Q - 1), sub, tmask, lane);
+        if (a < 0) { k = nr; break; }
+        const int kk = wt_block_of_bit(w, a) / w.Q;
+        if (w.Q == 1 || wt_count(w, kk) >= w.thr_reg) return kk;
+        k = kk + 1;
     }
-    for (; k < n; k++) if (wt_telo_count(w, k, wt_count(w, k))) return k;
+    if (k == nr && nr >= 0 && wt_telo_count(w, nr, wt_count(w, nr))) return nr;
     return n;
 }
 
-__device__ __noinline__ int next_telo_bwd(const WinTab &w, int k0)
+__device__ __noinline__ int next_telo_bwd(const WinTab &w, int k0, int sub, u32 tmask, int lane)
 {
     const int n = w.n;
     int k = k0 >= n ? n - 1 : k0;
     if (k < 0) return -1;
-    if (w.Q == 1) {
-        const u32 thr16 = (u32)w.thr_reg << 16;
-        if (k == n - 1) { if (wt_telo_count(w, k, wt_count(w, k))) return k; k--; }
-        while (k >= 0 && (k & 7) != 7) { if ((int)w.cnt[k] >= w.thr_reg) return k; k--; }
-        const uint4 *cv = reinterpret_cast<const uint4 *>(w.cnt);
-        while (k >= 31) {                                                /* windows k - 31 .. k, k % 8 == 7 */
-            const int g = k >> 3;
-            const uint4 v0 = __ldg(cv + g), v1 = __ldg(cv + g - 1), v2 = __ldg(cv + g - 2), v3 = __ldg(cv + g - 3);
-            if (quad_has_telo(v0, thr16) || quad_has_telo(v1, thr16) || quad_has_telo(v2, thr16) || quad_has_telo(v3, thr16)) break;
-            k -= 32;
-        }
-        while (k >= 0) { if ((int)w.cnt[k] >= w.thr_reg) return k; k--; }
-        return -1;
+    if (k == n - 1) { if (wt_telo_count(w, k, wt_count(w, k))) return k; k--; }
+    while (k >= 0) {
+        const long long a = team_last_bit(w.cls, wt_bit_of_block(w, 0), wt_bit_of_block(w, k * w.Q + w.Q - 1), sub, tmask, lane);
+        if (a < 0) return -1;
+        const int kk = wt_block_of_bit(w, a) / w.Q;
+        if (w.Q == 1 || wt_count(w, kk) >= w.thr_reg) return kk;
+        k = kk - 1;
     }
-    for (; k >= 0; k--) if (wt_telo_count(w, k, wt_count(w, k))) return k;
     return -1;
+}
+
+/* Eight consecutive windows (base, base + dir, ...), one per lane of the team: count and density (get_sub_density,
+ * NanoTel.R:467) are fetched / divided by all lanes at once and handed out by shuffles, so a run of telomeric windows
+ * costs one load and one division per eight windows instead of one dependent pair per window. */
+struct WinBuf { int base, dir, c; double d; };
+__device__ __forceinline__ void wb_get(WinBuf &b, const WinTab &w, int k, int dir, int sub, u32 tmask, int *c, double *d)
+{
+    int idx = (k - b.base) * dir;
+    if (b.dir != dir || idx < 0 || idx >= NTL_TEAM) {
+        b.base = k; b.dir = dir; idx = 0;
+        const int kk = k + dir * sub;
+        b.c = 0; b.d = 0.0;
+        if (kk >= 0 && kk < w.n) { b.c = wt_count(w, kk); b.d = wt_density_of_count(w, kk, b.c); }
+    }
+    *c = __shfl_sync(tmask, b.c, idx, NTL_TEAM);
+    *d = __shfl_sync(tmask, b.d, idx, NTL_TEAM);
 }
 
 /* find_telo_position (NanoTel.R:973-1077): forward scan for the first run of telomeric windows with in_a_row >= R
  * and score >= T, then the backward scan for the end.  Windows are 0-based here; non-telomeric windows only reset
  * the run state, so stretches of them are jumped over (next_telo_fwd / _bwd). */
-__device__ __noinline__ void find_telo_position(const WinTab &w, double R, double T, int *ps, int *pe)
+__device__ __noinline__ void find_telo_position(const WinTab &w, double R, double T, int *ps, int *pe, int sub, u32 tmask, int lane)
 {
     const int n = w.n;
     double score = 0.0;
     int start = -1, end = -1, in_a_row = 0;
     int end_position = 0;                                                /* 1-based i + 1 (:1022) */
+    WinBuf wb;
+    wb.base = 0; wb.dir = 0; wb.c = 0; wb.d = 0.0;
     for (int k = 0; k < n;) {                                            /* :1003-1025 */
-        const int c = wt_count(w, k);
+        int c; double dk;
+        wb_get(wb, w, k, 1, sub, tmask, &c, &dk);
         if (!wt_telo_count(w, k, c)) {
             score = 0.0; start = -1; in_a_row = 0;
             if (0.0 >= R && 0.0 >= T) { end_position = k + 2; break; }   /* never with the reference's R >= 3 */
-            k = next_telo_fwd(w, k + 1);
+            k = next_telo_fwd(w, k + 1, sub, tmask, lane);
             continue;
         }
         in_a_row += 1;
-        score = score + wt_density_of_count(w, k, c);                    /* :1014 */
+        score = score + dk;                                              /* :1014 */
         if (start == -1) start = wt_start(w, k);
         if ((double)in_a_row >= R && score >= T) { end_position = k + 2; break; }
         k++;
@@ -419,20 +501,21 @@ __device__ __noinline__ void find_telo_position(const WinTab &w, double R, doubl
     end = -1; score = 0.0; in_a_row = 0;
     if ((double)end_position >= (double)n - R + 1.0) {                   /* :1037-1044 */
         /* i = n; while (i > end_position && window i is not telomeric) i--  (1-based) */
-        int i = next_telo_bwd(w, n - 1) + 1;                             /* 1-based, 0 if none */
+        int i = next_telo_bwd(w, n - 1, sub, tmask, lane) + 1;                             /* 1-based, 0 if none */
         if (i < end_position) i = end_position;
         end = wt_end(w, (i < n ? i : n) - 1);                            /* end_position may be n + 1: the loop does not run */
     } else {                                                             /* :1046-1068 */
         for (int i = n; i >= end_position;) {
-            const int c = wt_count(w, i - 1);
+            int c; double dk;
+            wb_get(wb, w, i - 1, -1, sub, tmask, &c, &dk);
             if (!wt_telo_count(w, i - 1, c)) {
                 score = 0.0; end = -1; in_a_row = 0;
-                const int j = next_telo_bwd(w, i - 2) + 1;               /* 1-based */
+                const int j = next_telo_bwd(w, i - 2, sub, tmask, lane) + 1;               /* 1-based */
                 i = j;
                 continue;
             }
             in_a_row += 1;
-            score = score + wt_density_of_count(w, i - 1, c);
+            score = score + dk;
             if (end == -1) end = wt_end(w, i - 1);
             if ((double)in_a_row >= R && score >= T) break;
             i--;
@@ -481,45 +564,79 @@ __device__ __noinline__ void find_right_telo(const WinTab &w, int *ps, int *pe)
 }
 
 /* A TEAM of eight lanes works on one (candidate, track) item: the scalar state machines run on all eight lanes alike,
- * and where coverage has to be recomputed from the read every lane takes one word.
- * team_cov: coverage of track t (0 exact, 1 one mismatch, 2 one mismatch + TVR; the union of the trimmed hit intervals
- * of get_density_iranges, NanoTel.R:308-397) for virtual words w0 - 1 + sub (bit b of word w = position 32 w + b), one
- * word per lane: hit starts of every pattern in (previous word, word) dilated by the pattern length.  Lane 0 lacks the
- * hits of the word before its own: its word (w0 - 1) is only the look-behind; words w0 .. w0 + 6 are complete.
- * *hs = exact hit starts of main pattern 0 in the lane's word (the raw hit list of NanoTel.R:349-354). */
-#define NTL_TEAM 8
-__device__ __noinline__ u32 team_cov(const ReadView &rv, int t, int w0, int sub, u32 tmask, u32 *hs)
+ * and where coverage has to be recomputed from the read every lane takes one word (team_cov2 below): coverage of track
+ * t (0 exact, 1 one mismatch, 2 one mismatch + TVR; the union of the trimmed hit intervals of get_density_iranges,
+ * NanoTel.R:308-397) for virtual words w0 - 1 + sub (bit b of word w = position 32 w + b): hit starts of every pattern
+ * in (previous word, word) dilated by the pattern length.  Lane 0 lacks the hits of the word before its own: its word
+ * (w0 - 1) is only the look-behind; words w0 .. w0 + 6 are complete.  hs = exact hit starts of main pattern 0 in the
+ * lane's word (the raw hit list of NanoTel.R:349-354). */
+/* hit starts of one pattern in TWO words at once (word_hits for two independent positions: twice the instruction-level
+ * parallelism, one walk over the pattern's letter masks) */
+__device__ __forceinline__ void word_hits2(const ntl_dev_pat &pt, const u32 (&pwa)[4], const u32 (&pna)[4], const u32 (&pwb)[4],
+                                           const u32 (&pnb)[4], u32 *exa, u32 *lea, u32 *exb, u32 *leb)
 {
-    const int w = w0 - 1 + sub;
-    u32 pw[4], pn[4];
-    word_planes(rv, w, pw);
-    word_planes(rv, w + 1, pn);
-    u32 cov = 0u, h0 = 0u;
+    u32 o1 = 0u, t1 = 0u, o2 = 0u, t2 = 0u;
+    const bool fx = pt.fixed != 0;
+#pragma unroll 1
+    for (int j = 0; j < pt.m; j++) {
+        const u32 mA = pt.mux4[j][0], mC = pt.mux4[j][1], mG = pt.mux4[j][2], mT = pt.mux4[j][3];
+        u32 ewa, ena, ewb, enb;
+        if (fx) {
+            ewa = ~((pwa[0] ^ mA) | (pwa[1] ^ mC) | (pwa[2] ^ mG) | (pwa[3] ^ mT));
+            ena = ~((pna[0] ^ mA) | (pna[1] ^ mC) | (pna[2] ^ mG) | (pna[3] ^ mT));
+            ewb = ~((pwb[0] ^ mA) | (pwb[1] ^ mC) | (pwb[2] ^ mG) | (pwb[3] ^ mT));
+            enb = ~((pnb[0] ^ mA) | (pnb[1] ^ mC) | (pnb[2] ^ mG) | (pnb[3] ^ mT));
+        } else {
+            ewa = (pwa[0] & mA) | (pwa[1] & mC) | (pwa[2] & mG) | (pwa[3] & mT);
+            ena = (pna[0] & mA) | (pna[1] & mC) | (pna[2] & mG) | (pna[3] & mT);
+            ewb = (pwb[0] & mA) | (pwb[1] & mC) | (pwb[2] & mG) | (pwb[3] & mT);
+            enb = (pnb[0] & mA) | (pnb[1] & mC) | (pnb[2] & mG) | (pnb[3] & mT);
+        }
+        const u32 xa = ~__funnelshift_r(ewa, ena, j), xb = ~__funnelshift_r(ewb, enb, j);
+        t1 |= o1 & xa; o1 ^= xa;
+        t2 |= o2 & xb; o2 ^= xb;
+    }
+    *exa = ~(o1 | t1); *lea = ~t1;
+    *exb = ~(o2 | t2); *leb = ~t2;
+}
+
+/* team_cov for two independent word ranges (w0a - 1 + sub and w0b - 1 + sub) in one pass: the loads of both are in
+ * flight together and the two dependency chains interleave -- the locate kernel is bound by latency, not by issue. */
+__device__ __noinline__ void team_cov2(const ReadView &rv, int t, int w0a, int w0b, int sub, u32 tmask, u32 *cova, u32 *hsa,
+                                       u32 *covb, u32 *hsb)
+{
+    const int wa = w0a - 1 + sub, wb = w0b - 1 + sub;
+    u32 pwa[4], pna[4], pwb[4], pnb[4];
+    word_planes(rv, wa, pwa);
+    word_planes(rv, wa + 1, pna);
+    word_planes(rv, wb, pwb);
+    word_planes(rv, wb + 1, pnb);
+    u32 ca = 0u, cb = 0u, h0a = 0u, h0b = 0u;
 #pragma unroll 1
     for (int p = 0; p < c_prm.n_main; p++) {
-        u32 ex, le;
-        word_hits(c_prm.main_pat[p], pw, pn, &ex, &le);
-        if (p == 0) h0 = ex;
-        const u32 H = t >= 1 ? le : ex;
-        u32 Hp = __shfl_up_sync(tmask, H, 1, NTL_TEAM);
-        if (sub == 0) Hp = 0u;
+        u32 exa, lea, exb, leb;
+        word_hits2(c_prm.main_pat[p], pwa, pna, pwb, pnb, &exa, &lea, &exb, &leb);
+        if (p == 0) { h0a = exa; h0b = exb; }
+        const u32 Ha = t >= 1 ? lea : exa, Hb = t >= 1 ? leb : exb;
+        u32 Hpa = __shfl_up_sync(tmask, Ha, 1, NTL_TEAM), Hpb = __shfl_up_sync(tmask, Hb, 1, NTL_TEAM);
+        if (sub == 0) { Hpa = 0u; Hpb = 0u; }
 #pragma unroll 1
-        for (int j = 0; j < c_prm.main_pat[p].m; j++) cov |= __funnelshift_l(Hp, H, j);
+        for (int j = 0; j < c_prm.main_pat[p].m; j++) { ca |= __funnelshift_l(Hpa, Ha, j); cb |= __funnelshift_l(Hpb, Hb, j); }
     }
     if (t == 2) {
 #pragma unroll 1
         for (int p = 0; p < c_prm.n_tvr; p++) {
-            u32 ex, le;
-            word_hits(c_prm.tvr_pat[p], pw, pn, &ex, &le);
-            u32 Hp = __shfl_up_sync(tmask, ex, 1, NTL_TEAM);
-            if (sub == 0) Hp = 0u;
+            u32 exa, lea, exb, leb;
+            word_hits2(c_prm.tvr_pat[p], pwa, pna, pwb, pnb, &exa, &lea, &exb, &leb);
+            u32 Hpa = __shfl_up_sync(tmask, exa, 1, NTL_TEAM), Hpb = __shfl_up_sync(tmask, exb, 1, NTL_TEAM);
+            if (sub == 0) { Hpa = 0u; Hpb = 0u; }
 #pragma unroll 1
-            for (int j = 0; j < c_prm.tvr_pat[p].m; j++) cov |= __funnelshift_l(Hp, ex, j);
+            for (int j = 0; j < c_prm.tvr_pat[p].m; j++) { ca |= __funnelshift_l(Hpa, exa, j); cb |= __funnelshift_l(Hpb, exb, j); }
         }
     }
-    *hs = h0;
-    if (w < 0 || w >= rv.n_words) return 0u;
-    return cov & ntl_valid_word(w << 5, rv.L);          /* trim() to [1, L] */
+    *hsa = h0a; *hsb = h0b;
+    *cova = (wa < 0 || wa >= rv.n_words) ? 0u : ca & ntl_valid_word(wa << 5, rv.L);      /* trim() to [1, L] */
+    *covb = (wb < 0 || wb >= rv.n_words) ? 0u : cb & ntl_valid_word(wb << 5, rv.L);
 }
 
 /* bits of virtual word w that lie inside positions [lo, hi] */
@@ -570,20 +687,29 @@ __device__ __forceinline__ int team_bits_popc(u32 bits, int w0, int sub, u32 tma
     return team_sum(sub == 0 ? 0 : __popc(bits & word_range_mask(w0 - 1 + sub, lo, hi)), tmask);
 }
 
-/* covered positions of track t inside [lo, hi] (1 <= lo <= hi <= L), recomputed from the read, 7 words per step */
-__device__ __noinline__ int local_count(const ReadView &rv, int t, int lo, int hi, int sub, u32 tmask)
+/* covered positions of track t inside [lo1, hi1] and [lo2, hi2] (each 1 <= lo <= hi <= L, or empty: hi < lo),
+ * recomputed from the read, 7 words of each range per step */
+__device__ __noinline__ int local_count2(const ReadView &rv, int t, int lo1, int hi1, int lo2, int hi2, int sub, u32 tmask)
 {
     int total = 0;
-    for (int w0 = lo >> 5; w0 <= (hi >> 5); w0 += NTL_TEAM - 1) {
-        u32 hs;
-        const u32 cov = team_cov(rv, t, w0, sub, tmask, &hs);
-        total += team_bits_popc(cov, w0, sub, tmask, lo, hi);
+    int wa = lo1 >> 5, wb = lo2 >> 5;
+    const int ea = hi1 < lo1 ? wa - 1 : hi1 >> 5, eb = hi2 < lo2 ? wb - 1 : hi2 >> 5;
+    while (wa <= ea || wb <= eb) {
+        u32 ca, cb, ha, hb;
+        team_cov2(rv, t, wa, wb, sub, tmask, &ca, &ha, &cb, &hb);
+        int part = 0;
+        if (sub != 0) {
+            if (wa <= ea) part += __popc(ca & word_range_mask(wa - 1 + sub, lo1, hi1));
+            if (wb <= eb) part += __popc(cb & word_range_mask(wb - 1 + sub, lo2, hi2));
+        }
+        total += team_sum(part, tmask);
+        wa += NTL_TEAM - 1; wb += NTL_TEAM - 1;
     }
     return total;
 }
 
 /* covered bases of track t inside [a, b] (get_sub_density's numerator, NanoTel.R:467): whole blocks come from K2's
- * counts, the partial blocks at the two ends are recomputed from the read. */
+ * counts, the partial blocks at the two ends are recomputed from the read (both in one pass). */
 __device__ __noinline__ int covered_in(const ReadView &rv, const WinTab &w, int t, int a, int b, int sub, u32 tmask)
 {
     const int lo = a < 1 ? 1 : a, hi = b > rv.L ? rv.L : b;
@@ -594,12 +720,16 @@ __device__ __noinline__ int covered_in(const ReadView &rv, const WinTab &w, int 
     const int blo_s = blo * SG + 1, bhi_e = (bhi + 1) * SG < rv.L ? (bhi + 1) * SG : rv.L;
     if (blo == bhi) {
         if (lo == blo_s && hi == bhi_e) return (int)w.cnt[blo];
-        return local_count(rv, t, lo, hi, sub, tmask);
+        return local_count2(rv, t, lo, hi, 1, 0, sub, tmask);
     }
-    int total = 0, bf = blo, bl = bhi;
-    if (lo != blo_s) { total += local_count(rv, t, lo, (blo + 1) * SG, sub, tmask); bf = blo + 1; }
-    if (hi != bhi_e) { total += local_count(rv, t, bhi * SG + 1, hi, sub, tmask); bl = bhi - 1; }
-    for (int j = bf; j <= bl; j++) total += (int)w.cnt[j];
+    int bf = blo, bl = bhi;
+    int l1 = 1, h1 = 0, l2 = 1, h2 = 0;
+    if (lo != blo_s) { l1 = lo; h1 = (blo + 1) * SG; bf = blo + 1; }
+    if (hi != bhi_e) { l2 = bhi * SG + 1; h2 = hi; bl = bhi - 1; }
+    int part = 0;                                       /* whole blocks: every lane of the team sums an eighth of them */
+    for (int j = bf + sub; j <= bl; j += NTL_TEAM) part += (int)w.cnt[j];
+    int total = team_sum(part, tmask);
+    if (h1 >= l1 || h2 >= l2) total += local_count2(rv, t, l1, h1, l2, h2, sub, tmask);
     return total;
 }
 
@@ -609,98 +739,114 @@ __device__ __forceinline__ double density_of(const ReadView &rv, const WinTab &w
     return cv == 0 ? 0.0 : k3_div((double)cv, (double)(b - a + 1));      /* 0 / width is +0.0 exactly */
 }
 
-/* get_accurate_end (NanoTel.R:1692-1721).  `ranges` are the raw exact hits of the single fixed pattern on track A
- * (NanoTel.R:349-354) and the reduced runs of the coverage otherwise (:341-345). */
-__device__ __noinline__ int get_accurate_end(const ReadView &rv, int t, int telo_end, int sub, u32 tmask)
+/* get_accurate_start (NanoTel.R:1726-1764) and get_accurate_end (:1692-1721) together: the two are independent, so
+ * their coverage blocks are computed in one pass (team_cov2).  `ranges` are the raw exact hits of the single fixed
+ * pattern on track A (NanoTel.R:349-354) and the reduced runs of the coverage otherwise (:341-345). */
+__device__ __noinline__ void get_accurate_both(const ReadView &rv, int t, int telo_start, int telo_end, int sub, u32 tmask,
+                                               int *p_start, int *p_end)
 {
-    if (telo_end == -1) return -1;
-    /* range ends inside [e - 99, e + 50]: the words holding [e - 99, e + 51] (at most 6) are lanes 1 .. 7 */
-    const int w0 = (telo_end - 99) >> 5;
-    u32 hs;
-    const u32 cov = team_cov(rv, t, w0, sub, tmask, &hs);
-    u32 en;
-    if (t == 0 && c_prm.raw_hits_A) {
-        const u32 hp = __shfl_up_sync(tmask, hs, 1, NTL_TEAM);
-        en = __funnelshift_l(hp, hs, c_prm.main_pat[0].m - 1);           /* end = start + m - 1 */
-    } else {
-        u32 nx = __shfl_down_sync(tmask, cov, 1, NTL_TEAM);
-        if (sub == NTL_TEAM - 1) nx = 0u;                                /* lane 7's word is beyond e + 51: only a look-ahead */
-        en = cov & ~((cov >> 1) | (nx << 31));
-    }
-    int e_index = telo_end;
-    const int m1 = team_bits_max(en, w0, sub, tmask, telo_end - 99, telo_end);
-    if (m1 != NTL_NONE) e_index = m1;
-    const int m2 = team_bits_max(en, w0, sub, tmask, telo_end + 1, telo_end + 50);
-    if (m2 != NTL_NONE) e_index = m2;
-    return e_index;
-}
-
-/* get_accurate_start (NanoTel.R:1726-1764) */
-__device__ __noinline__ int get_accurate_start(const ReadView &rv, int t, int telo_start, int sub, u32 tmask)
-{
-    if (telo_start == -1) return telo_start;
+    if (telo_start == -1 && telo_end == -1) { *p_start = -1; *p_end = -1; return; }
     const int s = telo_start;
-    /* range starts inside [s - 36, s + 99]: the words holding [s - 37, s + 99] (at most 6) are lanes 1 .. 7 */
-    const int w0 = (s - 37) >> 5;
-    u32 hs;
-    const u32 cov = team_cov(rv, t, w0, sub, tmask, &hs);
-    u32 st;
-    if (t == 0 && c_prm.raw_hits_A) st = hs;
-    else {
-        const u32 pv = __shfl_up_sync(tmask, cov, 1, NTL_TEAM);          /* lane 1 looks behind into lane 0's (incomplete) word:
+    /* range starts inside [s - 36, s + 99]: the words holding [s - 37, s + 99] (at most 6) are lanes 1 .. 7;
+     * range ends inside [e - 99, e + 50]: the words holding [e - 99, e + 51] (at most 6) are lanes 1 .. 7 */
+    const int w0s = (s - 37) >> 5, w0e = (telo_end - 99) >> 5;
+    u32 cov, hs, cove, hse;
+    team_cov2(rv, t, w0s, w0e, sub, tmask, &cov, &hs, &cove, &hse);
+    /* ---- start */
+    if (telo_start != -1) {
+        u32 st;
+        if (t == 0 && c_prm.raw_hits_A) st = hs;
+        else {
+            const u32 pv = __shfl_up_sync(tmask, cov, 1, NTL_TEAM);      /* lane 1 looks behind into lane 0's (incomplete) word:
                                                                             only bit 32 w0 could be wrong, and it is < s - 36 */
-        st = cov & ~((cov << 1) | (pv >> 31));
-    }
-    const int c50 = team_bits_popc(cov, w0, sub, tmask, s, s + 49);
-    const double first_50 = k3_div((double)c50, 50.0);                         /* IRanges(start, width = 50) :1732 */
-    if (first_50 < 0.3) {
-        const int a = team_bits_min(st, w0, sub, tmask, s + 48, s + 99);
-        if (a != NTL_NONE) telo_start = a;
-        const int b = team_bits_min(st, w0, sub, tmask, s + 33, s + 48);
-        if (b != NTL_NONE) telo_start = b;
-    } else {
-        const int a = team_bits_min(st, w0, sub, tmask, s, s + 99);
-        if (a != NTL_NONE) telo_start = a;
-        if (first_50 >= 0.72) {
-            const int b = team_bits_min(st, w0, sub, tmask, s - 36, s - 1);
+            st = cov & ~((cov << 1) | (pv >> 31));
+        }
+        const int c50 = team_bits_popc(cov, w0s, sub, tmask, s, s + 49);
+        const double first_50 = k3_div((double)c50, 50.0);               /* IRanges(start, width = 50) :1732 */
+        if (first_50 < 0.3) {
+            const int a = team_bits_min(st, w0s, sub, tmask, s + 48, s + 99);
+            if (a != NTL_NONE) telo_start = a;
+            const int b = team_bits_min(st, w0s, sub, tmask, s + 33, s + 48);
             if (b != NTL_NONE) telo_start = b;
+        } else {
+            const int a = team_bits_min(st, w0s, sub, tmask, s, s + 99);
+            if (a != NTL_NONE) telo_start = a;
+            if (first_50 >= 0.72) {
+                const int b = team_bits_min(st, w0s, sub, tmask, s - 36, s - 1);
+                if (b != NTL_NONE) telo_start = b;
+            }
         }
     }
-    return telo_start;
+    /* ---- end */
+    int e_index = telo_end;
+    if (telo_end != -1) {
+        u32 en;
+        if (t == 0 && c_prm.raw_hits_A) {
+            const u32 hp = __shfl_up_sync(tmask, hse, 1, NTL_TEAM);
+            en = __funnelshift_l(hp, hse, c_prm.main_pat[0].m - 1);      /* end = start + m - 1 */
+        } else {
+            u32 nx = __shfl_down_sync(tmask, cove, 1, NTL_TEAM);
+            if (sub == NTL_TEAM - 1) nx = 0u;                            /* lane 7's word is beyond e + 51: only a look-ahead */
+            en = cove & ~((cove >> 1) | (nx << 31));
+        }
+        const int m1 = team_bits_max(en, w0e, sub, tmask, telo_end - 99, telo_end);
+        if (m1 != NTL_NONE) e_index = m1;
+        const int m2 = team_bits_max(en, w0e, sub, tmask, telo_end + 1, telo_end + 50);
+        if (m2 != NTL_NONE) e_index = m2;
+    }
+    *p_start = telo_start; *p_end = e_index;
 }
 
 /* One 18-bp window of search_left/right_patterns (multi_pattern_step_*, NanoTel.R:496-575, :614, :676):
  * matchPattern on subseq(read, a, b) with the default fixed = TRUE, the window's own out-of-bounds rule, hits not
- * trimmed.  Returns false if no pattern hits.
+ * trimmed.
  * The window and every alignment that can hit it (starts a - k .. b - m + 1 + k) fit one 32-bit word whose bit i is
  * position a - 1 + i: the word is cut out of two position words (the same for all lanes), letters outside [a, b] carry
  * zero masks (mismatches), and all alignment starts of a pattern are decided together by a two-plane mismatch counter
- * (Shift-And).  No shuffles: every lane computes the same value. */
-__device__ __noinline__ bool step_window(const ReadView &rv, int a, int b, int k, bool use_tvr, int *min_start, int *max_end)
+ * (Shift-And).  No shuffles: every lane computes the same value.
+ * The right-hand and the left-hand search of a track are independent, so one call serves a window of each (R, L):
+ * their loads are in flight together and the two match chains interleave.  on = false: that side is finished. */
+__device__ __forceinline__ void window_planes(const ReadView &rv, bool on, int a, int b, u32 (&pl)[4])
 {
-    *min_start = 0; *max_end = 0;
-    if (b < a) return false;
-    const int q0 = a - 1;                               /* position of bit 0 */
-    const int rb = q0 - 1;                              /* its index in the packed stream (position p = bit p - 1) */
-    u32 pl[4];
-    {
-        const int x = rb >> 5, sh = rb & 31;            /* rb = -1 (a = 1): x = -1, sh = 31 -> the stream shifted up by one */
-        const int NP = rv.fmt ? 4 : 2;
-        u32 w[4] = {0u, 0u, 0u, 0u};
+    pl[0] = pl[1] = pl[2] = pl[3] = 0u;
+    if (!on || b < a) return;
+    const int rb = a - 2;                               /* index of bit 0 (position a - 1) in the packed stream (p = bit p - 1) */
+    const int x = rb >> 5, sh = rb & 31;                /* rb = -1 (a = 1): x = -1, sh = 31 -> the stream shifted up by one */
+    const int NP = rv.fmt ? 4 : 2;
+    u32 w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int p = 0; p < 4; p++)
-            if (p < NP) w[p] = __funnelshift_r(rv_raw(rv, p, x), rv_raw(rv, p, x + 1), sh);
-        const u32 vm = ((2u << (b - a)) - 1u) << 1;     /* bits 1 .. b - a + 1: the window itself */
-        if (rv.fmt == 0) {
-            pl[0] = ~w[1] & ~w[0] & vm; pl[1] = ~w[1] & w[0] & vm; pl[2] = w[1] & w[0] & vm; pl[3] = w[1] & ~w[0] & vm;
-        } else {
+    for (int p = 0; p < 4; p++)
+        if (p < NP) w[p] = __funnelshift_r(rv_raw(rv, p, x), rv_raw(rv, p, x + 1), sh);
+    const u32 vm = ((2u << (b - a)) - 1u) << 1;         /* bits 1 .. b - a + 1: the window itself */
+    if (rv.fmt == 0) {
+        pl[0] = ~w[1] & ~w[0] & vm; pl[1] = ~w[1] & w[0] & vm; pl[2] = w[1] & w[0] & vm; pl[3] = w[1] & ~w[0] & vm;
+    } else {
 #pragma unroll
-            for (int p = 0; p < 4; p++) pl[p] = w[p] & vm;
-        }
+        for (int p = 0; p < 4; p++) pl[p] = w[p] & vm;
     }
-    const u32 vmask = ((2u << (b - a)) - 1u) << 1;
-    bool any = false;
-    int mn = 0, mx = 0;
+}
+
+struct WinHit { bool any; int mn, mx; };
+__device__ __forceinline__ void hit_update(WinHit &h, u32 bits, int q0, int m)
+{
+    if (!bits) return;
+    const int lo = q0 + __ffs((int)bits) - 1;
+    const int hi = q0 + 31 - __clz((int)bits) + m - 1;
+    if (!h.any || lo < h.mn) h.mn = lo;
+    if (!h.any || hi > h.mx) h.mx = hi;
+    h.any = true;
+}
+
+__device__ __noinline__ void step_window2(const ReadView &rv, bool onR, int aR, int bR, bool onL, int aL, int bL, int k,
+                                          bool use_tvr, WinHit *hR, WinHit *hL)
+{
+    WinHit R, Lh;
+    R.any = false; R.mn = 0; R.mx = 0; Lh.any = false; Lh.mn = 0; Lh.mx = 0;
+    onR = onR && bR >= aR; onL = onL && bL >= aL;
+    u32 pr[4], pq[4];
+    window_planes(rv, onR, aR, bR, pr);
+    window_planes(rv, onL, aL, bL, pq);
+    const u32 vmR = onR ? ((2u << (bR - aR)) - 1u) << 1 : 0u, vmL = onL ? ((2u << (bL - aL)) - 1u) << 1 : 0u;
     for (int pass = 0; pass < 2; pass++) {
         const int np = pass == 0 ? c_prm.n_main : (use_tvr ? c_prm.n_tvr : 0);
         const int kk = pass == 0 ? k : 0;
@@ -708,64 +854,67 @@ __device__ __noinline__ bool step_window(const ReadView &rv, int a, int b, int k
             const ntl_dev_pat &pt = pass == 0 ? c_prm.main_pat[p] : c_prm.tvr_pat[p];
             const int m = pt.m;
             /* alignment starts a - kk .. b - m + 1 + kk  <->  bits 1 - kk .. b - a + 2 - m + kk */
-            const int hi_bit = b - a + 2 - m + kk;
-            if (hi_bit < 1 - kk) continue;
-            u32 ones = 0u, twos = 0u;
+            const int hbR = bR - aR + 2 - m + kk, hbL = bL - aL + 2 - m + kk;
+            const bool doR = onR && hbR >= 1 - kk, doL = onL && hbL >= 1 - kk;
+            if (!doR && !doL) continue;
+            u32 o1 = 0u, t1 = 0u, o2 = 0u, t2 = 0u;
             for (int j = 0; j < m; j++) {
                 /* fixed = TRUE: the read's code must EQUAL the pattern letter's code */
                 const u32 mA = pt.mux4[j][0], mC = pt.mux4[j][1], mG = pt.mux4[j][2], mT = pt.mux4[j][3];
-                const u32 e = ~((pl[0] ^ mA) | (pl[1] ^ mC) | (pl[2] ^ mG) | (pl[3] ^ mT)) & vmask;
-                const u32 x = ~(e >> j);
-                twos |= ones & x;
-                ones ^= x;
+                const u32 e1 = ~((pr[0] ^ mA) | (pr[1] ^ mC) | (pr[2] ^ mG) | (pr[3] ^ mT)) & vmR;
+                const u32 e2 = ~((pq[0] ^ mA) | (pq[1] ^ mC) | (pq[2] ^ mG) | (pq[3] ^ mT)) & vmL;
+                const u32 x1 = ~(e1 >> j), x2 = ~(e2 >> j);
+                t1 |= o1 & x1; o1 ^= x1;
+                t2 |= o2 & x2; o2 ^= x2;
             }
-            const u32 sm = ((2u << hi_bit) - 1u) & ~((1u << (1 - kk)) - 1u);
-            const u32 h = (kk ? ~twos : ~(ones | twos)) & sm;
-            if (h) {
-                const int lo = q0 + __ffs((int)h) - 1;
-                const int hi = q0 + 31 - __clz((int)h) + m - 1;
-                if (!any || lo < mn) mn = lo;
-                if (!any || hi > mx) mx = hi;
-                any = true;
+            if (doR) {
+                const u32 sm = ((2u << hbR) - 1u) & ~((1u << (1 - kk)) - 1u);
+                hit_update(R, (kk ? ~t1 : ~(o1 | t1)) & sm, aR - 1, m);
+            }
+            if (doL) {
+                const u32 sm = ((2u << hbL) - 1u) & ~((1u << (1 - kk)) - 1u);
+                hit_update(Lh, (kk ? ~t2 : ~(o2 | t2)) & sm, aL - 1, m);
             }
         }
     }
-    *min_start = mn; *max_end = mx;
-    return any;
+    *hR = R; *hL = Lh;
 }
 
-/* search_left_patterns (NanoTel.R:576-633) */
-__device__ __noinline__ int search_left(const ReadView &rv, int start_index, int k, bool use_tvr)
-{
-    int subseq_start = start_index - 18 > 1 ? start_index - 18 : 1;
-    int new_start = start_index;
-    for (int i = 0; i < 4; i++) {
-        const int curr_end = subseq_start + 17 < rv.L ? subseq_start + 17 : rv.L;
-        int mn, mx;
-        if (!step_window(rv, subseq_start, curr_end, k, use_tvr, &mn, &mx)) break;
-        new_start = mn;
-        const int nn = subseq_start - 9 > 1 ? subseq_start - 9 : 1;
-        if (nn == subseq_start) break;
-        subseq_start = nn;
-    }
-    return new_start;
-}
-
-/* search_right_patterns (NanoTel.R:635-697) */
-__device__ __noinline__ int search_right(const ReadView &rv, int end_index, int k, bool use_tvr)
+/* search_right_patterns (NanoTel.R:635-697) from end_index and search_left_patterns (:576-633) from start_index,
+ * side by side.  doR / doL = false: that search is not wanted (the caller keeps its own value). */
+__device__ __noinline__ void search_both(const ReadView &rv, bool doR, int end_index, bool doL, int start_index, int k,
+                                         bool use_tvr, int *p_end, int *p_start)
 {
     int subseq_end = end_index + 18 < rv.L ? end_index + 18 : rv.L;
     int new_end = end_index;
-    for (int i = 0; i < 4; i++) {
-        const int curr_start = subseq_end - 17 > 1 ? subseq_end - 17 : 1;
-        int mn, mx;
-        if (!step_window(rv, curr_start, subseq_end, k, use_tvr, &mn, &mx)) break;
-        new_end = mx;
-        const int nn = subseq_end + 11 < rv.L ? subseq_end + 11 : rv.L;
-        if (nn == subseq_end) break;
-        subseq_end = nn;
+    int subseq_start = start_index - 18 > 1 ? start_index - 18 : 1;
+    int new_start = start_index;
+    bool onR = doR, onL = doL;
+    for (int i = 0; i < 4 && (onR || onL); i++) {
+        const int curr_start = subseq_end - 17 > 1 ? subseq_end - 17 : 1;              /* right: [curr_start, subseq_end] */
+        const int curr_end = subseq_start + 17 < rv.L ? subseq_start + 17 : rv.L;      /* left:  [subseq_start, curr_end] */
+        WinHit hR, hL;
+        step_window2(rv, onR, curr_start, subseq_end, onL, subseq_start, curr_end, k, use_tvr, &hR, &hL);
+        if (onR) {
+            if (!hR.any) onR = false;
+            else {
+                new_end = hR.mx;
+                const int nn = subseq_end + 11 < rv.L ? subseq_end + 11 : rv.L;
+                if (nn == subseq_end) onR = false;
+                subseq_end = nn;
+            }
+        }
+        if (onL) {
+            if (!hL.any) onL = false;
+            else {
+                new_start = hL.mn;
+                const int nn = subseq_start - 9 > 1 ? subseq_start - 9 : 1;
+                if (nn == subseq_start) onL = false;
+                subseq_start = nn;
+            }
+        }
     }
-    return new_end;
+    *p_end = new_end; *p_start = new_start;
 }
 
 /* =============================================================================================================
@@ -810,19 +959,15 @@ __device__ __forceinline__ bool triage_first_window_hit(u32 lo, u32 hi, int T)
     return any;
 }
 
-/* Eight lanes per read ("team"), four reads per warp: the team walks the block counts of the read's LAST track
- * (see below) 32 16-byte groups at a time (four independent loads per lane, 512 contiguous bytes per team and step),
- * so the longest read costs n_win / 256 dependent steps, and the loads of a team coalesce. */
-__global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
+/* One THREAD per read, reads in input order (coalesced tables and records).  The thread walks the class bits of the
+ * regular windows' blocks on the read's LAST track (see below): 32 blocks per word, four independent loads per step;
+ * a 20 kb read with 100-base windows is seven words. */
+__global__ void __launch_bounds__(128) ntl_triage_kernel(const ntl_read_args a)
 {
     const int lane = threadIdx.x & 31;
-    const int sub = lane & 7;
-    const u32 tmask = 0xffu << (lane & 24);
-    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
     bool cand = false;
-    int r = -1;
-    if (slot < a.n_reads) {
-        r = a.order[slot];
+    if (r < a.n_reads) {
         const int S = c_prm.S, T = c_prm.n_tracks, Q = c_prm.Q, SG = c_prm.SG;
         const int L = a.len[r];
         const int n_win = ntl_nwin(L, S);
@@ -841,57 +986,40 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
             if (simple)
                 simple = c_prm.right_edge ? ((n_win >= 2 ? S : L) < L - 200) : (1 + (n_win - 1) * S > 200);
             if (simple) {
-                /* any window with  !(count / width < min_density)  on any track?  Every read's block range starts
-                 * on a multiple of 8 entries, so groups of 8 counts are 16-byte aligned. */
-                const int thr_reg = c_prm.thr_reg;
-                const u32 thr16 = (u32)thr_reg << 16;
-                const int thr_last = (int)a.thr[L - (n_win - 1) * S];
-                bool tel = false;
-                /* The coverage of the tracks is nested (exact hits c <=1-mismatch hits c those + TVR hits), so a
+                /* any window with  !(count / width < min_density)  on any track?
+                 * The coverage of the tracks is nested (exact hits c <=1-mismatch hits c those + TVR hits), so a
                  * window's covered count can only grow from track to track: some track has a telomeric window iff
-                 * the LAST track has one.  Only that plane is walked: half (a third) of the bytes. */
-                const uint16_t *cm = a.cnt[T - 1] + wo;
-                int k_done = 0;                                  /* regular windows decided by the vector walk */
-                if (Q == 1) {
-                    const uint4 *cv = reinterpret_cast<const uint4 *>(cm);
-                    const int full = (n_win - 1) >> 3;           /* groups made of width-S windows only */
-                    constexpr int NJ = 4;                        /* independent 16-byte loads in flight per lane */
-                    for (int g0 = 0; g0 < full; g0 += 8 * NJ) {
-                        uint4 vv[NJ];
-#pragma unroll
-                        for (int j = 0; j < NJ; j++) {
-                            const int g = g0 + 8 * j + sub;
-                            vv[j] = g < full ? __ldg(cv + g) : make_uint4(0u, 0u, 0u, 0u);
-                        }
-#pragma unroll
-                        for (int j = 0; j < NJ; j++) {
-                            /* two counts per word: the upper one decides  x >= thr << 16, the lower one after a shift */
-                            const u32 x[4] = {vv[j].x, vv[j].y, vv[j].z, vv[j].w};
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                tel |= x[q] >= thr16;
-                                tel |= (x[q] << 16) >= thr16;
-                            }
-                        }
-                    }
-                    k_done = full << 3;
+                 * the LAST track has one.  The regular windows are decided by the class bits of that track's blocks
+                 * (for Q > 1 a set bit only says "maybe": the read goes to the locate kernel, which does not mind);
+                 * the last window (own width and threshold) by its count. */
+                const int thr_last = (int)a.thr[L - (n_win - 1) * S];
+                const int bps = c_prm.cls_bps;
+                const u32 *cl = reinterpret_cast<const u32 *>(a.cls[T - 1]);
+                const int nrb = (n_win - 1) * Q;                 /* blocks of the regular windows */
+                int c_last = 0;                                  /* requested before the bit walk, used after it */
+                {
+                    const uint16_t *cm = a.cnt[T - 1] + wo;
+                    for (int b = nrb; b < nb; b++) c_last += (int)cm[b];
                 }
-                /* the remaining windows, one per lane and step: regular windows are Q blocks, the last one (own width
-                 * and threshold) is every block that is left */
-                for (int k = k_done + sub; k < n_win; k += 8) {
-                    const int b0 = k * Q, b1 = k == n_win - 1 ? nb : b0 + Q;
-                    int c = 0;
-                    for (int b = b0; b < b1; b++) c += (int)cm[b];
-                    tel |= c >= (k == n_win - 1 ? thr_last : thr_reg);
+                u32 acc = 0u;
+                if (nrb > 0) {
+                    const long long b0 = bps == 8 ? wo : wo / bps * 8;
+                    const long long a_lo = b0, a_hi = bps == 8 ? b0 + nrb - 1 : b0 + (long long)((nrb - 1) / bps) * 8 + (nrb - 1) % bps;
+                    const long long w_lo = a_lo >> 5, w_hi = a_hi >> 5;
+                    /* first and last word under their masks, the words between them whole */
+                    acc = cls_word(cl, w_lo, a_lo, a_hi) | cls_word(cl, w_hi, a_lo, a_hi);
+                    long long wi = w_lo + 1;
+                    for (; wi + 4 <= w_hi; wi += 4)
+                        acc |= (__ldg(cl + wi) | __ldg(cl + wi + 1)) | (__ldg(cl + wi + 2) | __ldg(cl + wi + 3));
+                    for (; wi < w_hi; wi++) acc |= __ldg(cl + wi);
                 }
-                simple = (__ballot_sync(tmask, tel) & tmask) == 0u;
+                simple = acc == 0u && c_last < thr_last;
             }
             if (simple) simple = !triage_first_window_hit(lo0 << 1, hi0 << 1, T);
             if (!simple) cand = true;
         }
         if (!cand) {
-            /* the 64-byte record goes out as four 16-byte stores from lanes 0..3 of the team */
-            alignas(16) ntl_read_result o;       /* stored below as four 16-byte pieces */
+            alignas(16) ntl_read_result o;       /* stored as four 16-byte pieces */
             o.status = status;
             o.n_win = n_win > 0 ? n_win : 0;
             for (int t = 0; t < 3; t++) {
@@ -899,25 +1027,25 @@ __global__ void __launch_bounds__(256) ntl_triage_kernel(const ntl_read_args a)
                 o.track[t].start = live ? -1 : 0; o.track[t].end = 0; o.track[t].density = 0.0;
             }
             o.win_offset = wo;
-            if (sub < 4)
-                reinterpret_cast<uint4 *>(reinterpret_cast<ntl_read_result *>(a.results) + r)[sub] =
-                    reinterpret_cast<const uint4 *>(&o)[sub];
-            if (a.stages != nullptr && status == 0 && sub < T) {
+            uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<ntl_read_result *>(a.results) + r);
+#pragma unroll
+            for (int q = 0; q < 4; q++) dst[q] = reinterpret_cast<const uint4 *>(&o)[q];
+            if (a.stages != nullptr && status == 0) {
                 ntl_stage s;
                 s.coarse_start = s.coarse_end = s.acc_start = s.acc_end = s.edge_start = s.edge_end = -1;
                 s.acc_density = 0.0;
-                reinterpret_cast<ntl_stage *>(a.stages)[(size_t)r * 3 + sub] = s;
+                for (int t = 0; t < T; t++) reinterpret_cast<ntl_stage *>(a.stages)[(size_t)r * 3 + t] = s;
             }
         }
     }
-    /* warp-aggregated append to the candidate list (one entry per team) */
-    const u32 cm = __ballot_sync(NTL_FULL, cand && sub == 0);
+    /* warp-aggregated append to the candidate list */
+    const u32 cm = __ballot_sync(NTL_FULL, cand);
     if (cm) {
         int base = 0;
         const int leader = __ffs((int)cm) - 1;
         if (lane == leader) base = (int)atomicAdd(&a.counters[0], (u32)__popc(cm));
         base = __shfl_sync(NTL_FULL, base, leader);
-        if (cand && sub == 0) {
+        if (cand) {
             const int pos = base + __popc(cm & ((1u << lane) - 1u));
             a.cand[pos] = r;
             reinterpret_cast<int4 *>(a.cand_state)[pos] = make_int4(0, 0, 0, 0);
@@ -939,6 +1067,7 @@ __device__ void locate_items(const ntl_read_args &a, bool valid, int r, int t, i
     WinTab w;
     rv.L = 0; rv.fmt = 0; rv.base = nullptr; rv.n_words = 0; rv.n_raw = 0; rv.ccov = nullptr; rv.cwb = nullptr;
     w.cnt = nullptr; w.n = 0; w.nb = 0; w.Q = 1; w.SG = 1; w.S = 1; w.L = 0; w.thr_reg = 0; w.thr_last = 0;
+    w.cls = nullptr; w.bit0 = 0; w.bps = 8;
     const int S = c_prm.S, T = c_prm.n_tracks;
     int n_win = 0, status = 0;
     ntl_track out;
@@ -950,6 +1079,7 @@ __device__ void locate_items(const ntl_read_args &a, bool valid, int r, int t, i
     const bool use_tvr = t == 2;
     ntl_stage *stg = nullptr;
 
+    K3CLK_BEGIN;
     /* ---- phase 0: tables, coarse interval (window scans: data dependent) */
     if (valid) {
         stg = a.stages ? reinterpret_cast<ntl_stage *>(a.stages) + (size_t)r * 3 : nullptr;
@@ -960,25 +1090,36 @@ __device__ void locate_items(const ntl_read_args &a, bool valid, int r, int t, i
         w.cnt = a.cnt[t] + a.cnt_off[r]; w.n = n_win > 0 ? n_win : 0; w.S = S; w.L = rv.L;
         w.Q = c_prm.Q; w.SG = c_prm.SG; w.nb = (rv.L + c_prm.SG - 1) / c_prm.SG;
         w.thr_reg = c_prm.thr_reg;
+        w.cls = reinterpret_cast<const u32 *>(a.cls[t]); w.bps = c_prm.cls_bps; w.bit0 = c_prm.cls_bps == 8 ? a.cnt_off[r] : a.cnt_off[r] / c_prm.cls_bps * 8;
         w.thr_last = w.n > 0 ? (int)a.thr[wt_end(w, w.n - 1) - wt_start(w, w.n - 1) + 1] : 0;
-        find_telo_position(w, 3.0, 2.0, &ts, &te);                                     /* :1084-1086 */
+    }
+    K3CLK(0);
+    if (valid) {
+        find_telo_position(w, 3.0, 2.0, &ts, &te, sub, tmask, threadIdx.x & 31);                                     /* :1084-1086 */
+    }
+    K3CLK(1);
+    double telo_density = 0.0;
+    if (valid) {
         /* the coarse interval is made of whole windows: its density needs no coverage recomputation */
-        const double telo_density = density_of(rv, w, t, ts, te, sub, tmask);          /* :1099 */
+        telo_density = density_of(rv, w, t, ts, te, sub, tmask);                       /* :1099 */
+    }
+    K3CLK(2);
+    if (valid) {
         const int num_rows = (te - ts + 1) / S;                                        /* :1103 */
         if (telo_density < 0.85 && num_rows > 5) {                                     /* :1104-1110 */
             const double min_rows = num_rows <= 7 ? (double)(num_rows - 2) : 7.0;
             const double min_score = 0.6 * min_rows;
-            find_telo_position(w, min_rows, min_score, &ts, &te);
+            find_telo_position(w, min_rows, min_score, &ts, &te, sub, tmask, threadIdx.x & 31);
         }
         cs = ts; ce = te;
     }
     __syncwarp();
-    /* ---- phase 1, 2: accurate start / end (one coverage block each) */
+    K3CLK(3);
+    /* ---- phase 1: accurate start and end (one coverage block each, computed side by side) */
     int start_acc = -1, end_acc = -1;
-    if (valid) start_acc = get_accurate_start(rv, t, ts, sub, tmask);                  /* :1119 */
+    if (valid) get_accurate_both(rv, t, ts, te, sub, tmask, &start_acc, &end_acc);     /* :1119-1120 */
     __syncwarp();
-    if (valid) end_acc = get_accurate_end(rv, t, te, sub, tmask);                      /* :1120 */
-    __syncwarp();
+    K3CLK(4);
     if (valid) {
         if (start_acc > end_acc) end_acc = start_acc;                                  /* :1122-1124 */
         ts = start_acc; te = end_acc;
@@ -998,12 +1139,21 @@ __device__ void locate_items(const ntl_read_args &a, bool valid, int r, int t, i
         }
     }
     __syncwarp();
-    /* ---- phase 3, 4: the 18-bp re-match searches */
-    if (valid && !err) e2 = te < rv.L ? search_right(rv, te + 1, k, use_tvr) : te;      /* :1140-1144 */
+    K3CLK(6);
+    /* ---- phase 2: the 18-bp re-match searches, right and left side by side */
+    if (valid && !err) {                                                               /* :1140-1149 */
+        e2 = te; s2 = ts;
+        const bool doR = te < rv.L, doL = ts > 1;
+        if (doR || doL) {
+            int e3, s3;
+            search_both(rv, doR, te + 1, doL, ts - 1, k, use_tvr, &e3, &s3);
+            if (doR) e2 = e3;
+            if (doL) s2 = s3;
+        }
+    }
     __syncwarp();
-    if (valid && !err) s2 = ts > 1 ? search_left(rv, ts - 1, k, use_tvr) : ts;          /* :1145-1149 */
-    __syncwarp();
-    /* ---- phase 5: final density (:1840-1844) */
+    K3CLK(7);
+    /* ---- phase 3: final density (:1840-1844) */
     if (valid && !err) {
         if (e2 < s2 - 1) err = true;                                                   /* IRanges() would stop */
         else {
@@ -1013,6 +1163,7 @@ __device__ void locate_items(const ntl_read_args &a, bool valid, int r, int t, i
         }
     }
     __syncwarp();
+    K3CLK(9);
     /* ---- this track is done; the team that completes the read's last track writes the record head:
      *      keep iff max interval width >= 30 over the tracks (:1847, :1857) */
     if (!valid || sub != 0) return;
@@ -1053,7 +1204,9 @@ __global__ void __launch_bounds__(64) ntl_locate_kernel(const ntl_read_args a)
         const int i = base + (lane >> 3);
         const bool valid = i < n_items;
         const int c = valid ? i / T : 0;
+        K3CLK_BEGIN;
         locate_items(a, valid, valid ? a.cand[c] : 0, valid ? i - c * T : 0, a.cand_state + 4 * (size_t)c, sub, tmask);
+        K3CLK(15);
     }
 }
 
@@ -1095,6 +1248,32 @@ __global__ void __launch_bounds__(256) ntl_scan_generic_kernel(const ntl_read_ar
     }
 }
 
+/* Class bits from the block counts, dense layout (cls_bps = 8: bit g = block g): one thread per byte.  Runs after a
+ * scan kernel that does not write the bits itself (the generic kernel; spans of more than 8 blocks). */
+__global__ void __launch_bounds__(256) ntl_cls_kernel(const ntl_read_args a, long long n_bytes, int T, u32 blk_thr)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bytes) return;
+    for (int t = 0; t < T; t++) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.cnt[t]) + i);
+        const u32 x[4] = {v.x, v.y, v.z, v.w};
+        u32 b = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if ((x[q] & 0xffffu) >= blk_thr) b |= 1u << (2 * q);
+            if ((x[q] >> 16) >= blk_thr) b |= 2u << (2 * q);
+        }
+        a.cls[t][i] = (uint8_t)b;
+    }
+}
+
+extern "C" cudaError_t ntl_k_cls(const ntl_read_args *a, long long n_bytes, int T, uint32_t blk_thr, cudaStream_t st)
+{
+    if (n_bytes <= 0) return cudaSuccess;
+    ntl_cls_kernel<<<(unsigned)((n_bytes + 255) / 256), 256, 0, st>>>(*a, n_bytes, T, blk_thr);
+    return cudaGetLastError();
+}
+
 /* =============================================================================================================
  * launchers (called from ntl_api.cpp)
  * ============================================================================================================= */
@@ -1132,7 +1311,7 @@ extern "C" cudaError_t ntl_k_items(const uint8_t *active, int n_items, int32_t *
 extern "C" cudaError_t ntl_k_triage(const ntl_read_args *a, cudaStream_t st)
 {
     if (a->n_reads <= 0) return cudaSuccess;
-    ntl_triage_kernel<<<(a->n_reads * 8 + 255) / 256, 256, 0, st>>>(*a);     /* 8 lanes per read */
+    ntl_triage_kernel<<<(a->n_reads + 127) / 128, 128, 0, st>>>(*a);             /* one thread per read */
     return cudaGetLastError();
 }
 

@@ -11,6 +11,16 @@
 #include <stdint.h>
 #include NTL_GENERATED_SOURCE
 
+/* class bytes (one per span and track, blocks per span <= 8): optional */
+static uint32_t blk_thr = 0xffffffffu;
+static uint8_t *cls_planes[3] = {nullptr, nullptr, nullptr};
+static uint8_t **cls = nullptr;
+extern "C" int span_model_set_cls(uint32_t thr, uint8_t *c0, uint8_t *c1, uint8_t *c2)
+{
+    blk_thr = thr; cls_planes[0] = c0; cls_planes[1] = c1; cls_planes[2] = c2; cls = c0 ? cls_planes : nullptr;
+    return 0;
+}
+
 template <int NPL>
 static void run_arena(const uint32_t *arena, int64_t n_spans, const uint8_t *flags, int n_reads, const int32_t *len,
                       const int64_t *woff, const uint8_t *fmt, int64_t cnt_base, uint16_t *c0, uint16_t *c1, uint16_t *c2)
@@ -22,7 +32,9 @@ static void run_arena(const uint32_t *arena, int64_t n_spans, const uint8_t *fla
         if (f & (NTL_SPAN_TAIL | NTL_SPAN_SKIP)) continue;
         uint16_t *out[3];
         for (int t = 0; t < 3; t++) out[t] = t < NTL_J_NTRACKS ? cnt[t] + (cnt_base + s * BPS) : nullptr;
-        ntl_span<NPL, false, W, SG>(arena + s * W * NPL, (f & NTL_SPAN_FIRST) != 0, 0, out);
+        u32 cb[3];
+        ntl_span<NPL, false, W, SG>(arena + s * W * NPL, (f & NTL_SPAN_FIRST) != 0, 0, out, blk_thr, cb);
+        if (cls && BPS <= 8) for (int t = 0; t < NTL_J_NTRACKS; t++) cls[t][cnt_base / BPS + s] = (uint8_t)cb[t];
     }
     for (int r = 0; r < n_reads; r++) {
         if ((fmt[r] != 0) != (NPL == 4)) continue;
@@ -35,7 +47,9 @@ static void run_arena(const uint32_t *arena, int64_t n_spans, const uint8_t *fla
         for (int s = s_lo; s < nsp; s++) {
             uint16_t *out[3];
             for (int t = 0; t < 3; t++) out[t] = t < NTL_J_NTRACKS ? cnt[t] + (cnt_base + (s_first + s) * BPS) : nullptr;
-            ntl_span<NPL, true, W, SG>(arena + (s_first + s) * W * NPL, s == 0, L - s * 32 * W, out);
+            u32 cb[3];
+            ntl_span<NPL, true, W, SG>(arena + (s_first + s) * W * NPL, s == 0, L - s * 32 * W, out, blk_thr, cb);
+            if (cls && BPS <= 8) for (int t = 0; t < NTL_J_NTRACKS; t++) cls[t][cnt_base / BPS + s_first + s] = (uint8_t)cb[t];
         }
     }
 }

@@ -99,6 +99,11 @@ def _run_and_compare(tmp, seqs, patterns, tvr, S, rc):
     (a2, l2), (a4, l4) = arenas
     M.span_model_run.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    # class bytes: one per span and track when a span holds at most 8 blocks; bit j <=> block j holds >= blk_thr bases
+    blk_thr = max(1, (int(np.ceil(0.6 * S)) + Q - 1) // Q)
+    cls = [np.full(nspans[0] + nspans[1] + 1, 0xff, np.uint8) for _ in range(3)]
+    M.span_model_set_cls.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    M.span_model_set_cls(blk_thr, cls[0].ctypes.data, cls[1].ctypes.data, cls[2].ctypes.data)
     M.span_model_run(a2.ctypes.data + 4 * l2, nspans[0], flags[0].ctypes.data, a4.ctypes.data + 4 * l4, nspans[1],
                      flags[1].ctypes.data, len(seqs), lens.ctypes.data, woff.ctypes.data, fmt.ctypes.data,
                      cnt[0].ctypes.data, cnt[1].ctypes.data, cnt[2].ctypes.data)
@@ -116,6 +121,14 @@ def _run_and_compare(tmp, seqs, patterns, tvr, S, rc):
                 k = [j for j in range(nw) if got[j] != exp[j]][0]
                 bad.append((i, len(s), t, k, got[k], exp[k]))
     assert not bad, bad[:8]
+    if BPS <= 8:
+        for i, s in enumerate(seqs):
+            nb = (len(s) + SG - 1) // SG
+            for t in range(T):
+                blk = cnt[t][cnt_off[i]: cnt_off[i] + nb].astype(np.int64)
+                by = cls[t][cnt_off[i] // BPS: cnt_off[i] // BPS + (nb + BPS - 1) // BPS]
+                got = np.array([(int(by[j // BPS]) >> (j % BPS)) & 1 for j in range(nb)], bool)
+                assert (got == (blk >= blk_thr)).all(), (i, len(s), t)
     return W, SG
 
 
