@@ -386,6 +386,14 @@ def main():
     res = res.copy()                                          # outside the timed region: later batches reuse the buffer
     n_keep = int((res["status"] & 1).sum())
 
+    # -- what the host's memory system gives the packer: every rank streams its own ASCII input with its own packer
+    #    threads at the same time (loads only: the packer's access pattern without arithmetic or stores)
+    from nanotel_b200 import _lib as _ntl_lib
+    barrier()
+    host_read_gbs = float(_ntl_lib.load().ntl_host_read_gbs(buf.ctypes.data, int(offsets[-1]), host_threads, 3)) if bases else 0.0
+    barrier()
+    host_rw_gbs = float(_ntl_lib.load().ntl_host_read_gbs(buf.ctypes.data, int(offsets[-1]), host_threads, -3)) if bases else 0.0
+
     # -- the same, starting from the packed reads in pinned host memory (H2D + kernels + D2H per step): what the
     #    path costs once the ASCII -> 2-bit packing is taken out (extra information, not the headline)
     sc.pack_concat(buf, offsets)
@@ -411,7 +419,7 @@ def main():
     # -- max over ranks; one digest per block, gathered on rank 0 (the host-side gather of the design, after the
     #    timed region; NCCL carries 8 bytes per block here, nothing on the data path)
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
-    b = torch.tensor([float(bases)], dtype=torch.float64, device="cuda")
+    b = torch.tensor([float(bases), host_read_gbs, bases / max(tm_e2e["pack_ms"], 1e-9) / 1e6, host_rw_gbs], dtype=torch.float64, device="cuda")
     dig = torch.zeros(max(n_blocks_total, 1), dtype=torch.int64, device="cuda")
     pos = 0
     for j, blk in enumerate(my_blocks):
@@ -453,6 +461,12 @@ def main():
                     "ms_per_step": e2e_s_max * 1e3, "steps": args.e2e_steps,
                     "breakdown_ms": {k: tm_e2e[k] for k in ("pack_ms", "h2d_ms", "filter_ms", "scan_ms", "locate_ms", "d2h_ms")},
                     "host_threads": host_threads, "host_cores": cores,
+                    "host_memory": {"read_gbs_all_ranks": float(b[1]), "read_write_gbs_all_ranks": float(b[3]),
+                                    "pack_gbs_all_ranks": float(b[2]),
+                                    "note": "GB/s of ASCII input moved by the packer threads of all ranks at once: plain "
+                                            "streaming reads; reads + a quarter-size non-temporal write (the packer's "
+                                            "traffic without its arithmetic); the packer itself inside the e2e steps "
+                                            "(where the DMA engine also reads 0.25 B per base)"},
                     "from_packed_pinned": {"value": bases / prepacked_s / 1e9, "unit": "Gbases/s (rank 0)",
                                            "ms_per_step": prepacked_s * 1e3},
                     "note": "pack (host, AVX2) and H2D overlap: h2d_ms spans first to last copy; per-rank h2d/d2h bytes"},

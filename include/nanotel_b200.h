@@ -48,7 +48,8 @@ typedef enum {
     NTL_ERR_CUDA = -4,           /* no device / CUDA runtime error (message has the CUDA string)   */
     NTL_ERR_NOMEM = -5,
     NTL_ERR_JIT = -6,            /* no specialised scan kernel (precompiled / cached / NVRTC) and NTL_OPT_REQUIRE_JIT was set */
-    NTL_ERR_STATE = -7           /* call order violated (e.g. ntl_batch_run before ntl_batch_pack) */
+    NTL_ERR_STATE = -7,          /* call order violated (e.g. ntl_batch_run before ntl_batch_pack) */
+    NTL_ERR_IO = -8              /* an output file could not be written (ntl_write_*)              */
 } ntl_status;
 
 /* ntl_params.options */
@@ -203,6 +204,20 @@ int32_t ntl_reader_next(ntl_reader *reader, int32_t nrec, const char **seq_buf, 
 const char *ntl_reader_error(const ntl_reader *reader);
 void ntl_reader_close(ntl_reader *reader);
 
+/* -- per-read output files (host side; replaces writeXStringSet + the tables handed to the plot functions,
+ *    NanoTel.R:1870-1918) ---------------------------------------------------------------------------------- */
+/* For every summary row j of the last batch (read order[j], Serial serial[order[j]]; ntl_assign_serials) write
+ *   <out_dir>/reads/<Serial>.fasta.gz            '>' + header line + the upper-case sequence, 80 letters per line
+ *                                                (reverse-complemented back if rc_applied), gzip level 6
+ *   <out_dir>/density_vectors/read<Serial>.csv   ID,start_index,end_index and density / class per track
+ * with `threads` host threads.  buf/offsets: the chunk's sequences as given to ntl_scan_batch_concat; names /
+ * name_off: the header lines, concatenated (n_reads + 1 offsets).  Returns NTL_OK or NTL_ERR_IO / NTL_ERR_ARG. */
+int ntl_write_read_outputs(const ntl_ctx *ctx, const char *out_dir, const char *buf, const int64_t *offsets,
+                           const char *names, const int64_t *name_off, const int32_t *serial, const int32_t *order,
+                           int32_t n_rows, int32_t n_tracks, double min_density, int32_t rc_applied, int32_t threads);
+/* One reads/<Serial>.fasta.gz as above (no context, no device). */
+int ntl_write_fasta_gz(const char *path, const char *name, const char *seq, int64_t len, int32_t rc);
+
 /* -- diagnostics ------------------------------------------------------------------------------------------ */
 /* NVRTC-compile the pattern-specialised scan kernel for `arch` ("sm_100a") without touching a device; optionally
  * write the cubin to cubin_path (for cuobjdump).  Returns the cubin size in bytes or a negative ntl_status. */
@@ -218,6 +233,12 @@ long ntl_jit_get_source(const ntl_params *params, char *buf, long cap);
  * positions, or {A, C, G, T} if the read holds a letter other than A/C/G/T: *four_bit = 1) to `words` (capacity in
  * 32-bit words) and returns the number of words written, negative on error.  Layout: csrc/ntl_dev.h. */
 long ntl_pack_read(const char *seq, int64_t len, int32_t rc, uint32_t *words, int64_t capacity, int32_t *four_bit);
+
+/* Rate (GB/s) at which `threads` host threads read `bytes` bytes at `buf` (AVX2 loads, 4 KiB software prefetch: the
+ * packer's own access pattern without its arithmetic or its stores), best of `reps` passes.  The ceiling of
+ * ntl_batch_pack on this host: bench.py prints it beside the packer's rate.  reps < 0: -reps passes that also write
+ * a quarter of the bytes with non-temporal stores (the packer's whole memory traffic).  No device needed. */
+double ntl_host_read_gbs(const void *buf, int64_t bytes, int32_t threads, int32_t reps);
 
 /* -- host-side helpers of the same path ------------------------------------------------------------------- */
 /* Serial numbers and row order of one chunk exactly as search_patterns + the 8-way split assign them

@@ -288,3 +288,78 @@ void ntl_parallel_for(int64_t n, int n_threads, int64_t grain, const std::functi
     worker();
     for (auto &t : th) t.join();
 }
+
+/* Diagnostics: the rate at which the host can stream the ASCII input (see nanotel_b200.h). */
+#include <chrono>
+__attribute__((target("avx2")))
+static uint64_t read_range_avx2(const unsigned char *p, int64_t b, int64_t e)
+{
+    __m256i v0 = _mm256_setzero_si256(), v1 = v0;
+    int64_t i = b;
+    for (; i + 64 <= e; i += 64) {
+        _mm_prefetch((const char *)p + i + 4096, _MM_HINT_T0);
+        v0 = _mm256_xor_si256(v0, _mm256_loadu_si256((const __m256i *)(p + i)));
+        v1 = _mm256_xor_si256(v1, _mm256_loadu_si256((const __m256i *)(p + i + 32)));
+    }
+    v0 = _mm256_xor_si256(v0, v1);
+    uint64_t acc = (uint64_t)_mm256_extract_epi64(v0, 0) ^ (uint64_t)_mm256_extract_epi64(v0, 1) ^
+                   (uint64_t)_mm256_extract_epi64(v0, 2) ^ (uint64_t)_mm256_extract_epi64(v0, 3);
+    for (; i < e; i++) acc ^= p[i];
+    return acc;
+}
+static uint64_t read_range_scalar(const unsigned char *p, int64_t b, int64_t e)
+{
+    uint64_t acc = 0;
+    int64_t i = b;
+    for (; i + 8 <= e; i += 8) { uint64_t v; memcpy(&v, p + i, 8); acc ^= v; }
+    for (; i < e; i++) acc ^= p[i];
+    return acc;
+}
+
+/* the packer's traffic without its arithmetic: 128 bytes read, 32 bytes written with a non-temporal store */
+__attribute__((target("avx2")))
+static uint64_t read_write_range_avx2(const unsigned char *p, int64_t b, int64_t e, unsigned char *out)
+{
+    __m256i acc = _mm256_setzero_si256();
+    int64_t i = b;
+    for (; i + 128 <= e; i += 128) {
+        _mm_prefetch((const char *)p + i + 4096, _MM_HINT_T0);
+        _mm_prefetch((const char *)p + i + 4096 + 64, _MM_HINT_T0);
+        const __m256i a0 = _mm256_loadu_si256((const __m256i *)(p + i)), a1 = _mm256_loadu_si256((const __m256i *)(p + i + 32));
+        const __m256i a2 = _mm256_loadu_si256((const __m256i *)(p + i + 64)), a3 = _mm256_loadu_si256((const __m256i *)(p + i + 96));
+        const __m256i x = _mm256_xor_si256(_mm256_xor_si256(a0, a1), _mm256_xor_si256(a2, a3));
+        _mm256_stream_si256((__m256i *)(out + (i >> 2)), x);
+        acc = _mm256_xor_si256(acc, x);
+    }
+    _mm_sfence();
+    return (uint64_t)_mm256_extract_epi64(acc, 0) ^ (uint64_t)_mm256_extract_epi64(acc, 3);
+}
+
+extern "C" double ntl_host_read_gbs(const void *buf, int64_t bytes, int32_t threads, int32_t reps)
+{
+    if (!buf || bytes <= 0) return 0.0;
+    if (threads < 1) threads = 1;
+    /* reps < 0: the read + quarter-size non-temporal write pattern of the packer, -reps passes */
+    const bool with_writes = reps < 0 && g_have_avx2;
+    if (reps < 0) reps = -reps;
+    if (reps < 1) reps = 1;
+    const unsigned char *p = (const unsigned char *)buf;
+    unsigned char *out = nullptr;
+    if (with_writes) {
+        if (posix_memalign((void **)&out, 64, (size_t)(bytes >> 2) + 256) != 0) return 0.0;
+        memset(out, 0, (size_t)(bytes >> 2) + 256);                        /* touch the pages before timing */
+    }
+    double best = 0.0;
+    std::atomic<uint64_t> sink(0);
+    for (int r = 0; r < reps; r++) {
+        const auto t0 = std::chrono::steady_clock::now();
+        ntl_parallel_for(bytes, threads, 1 << 20, [&](int64_t b, int64_t e) {
+            sink.fetch_xor(with_writes ? read_write_range_avx2(p, b, e, out)
+                                       : g_have_avx2 ? read_range_avx2(p, b, e) : read_range_scalar(p, b, e));
+        });
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (s > 0 && (double)bytes / s / 1e9 > best) best = (double)bytes / s / 1e9;
+    }
+    free(out);
+    return sink.load() == 0x5a5a5a5a5a5a5a5bULL ? best + 1e-9 : best;     /* keep the reads alive */
+}

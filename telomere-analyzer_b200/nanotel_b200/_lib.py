@@ -61,7 +61,7 @@ EXPORTS = [
     "ntl_scan_batch_pool", "ntl_scan_path", "ntl_scan_path_note", "ntl_device_count", "ntl_get_shards", "ntl_get_geometry",
     "ntl_jit_precompile_to", "ntl_jit_get_source",
     "ntl_batch_pack", "ntl_batch_upload", "ntl_batch_run", "ntl_batch_enqueue", "ntl_batch_wait", "ntl_batch_download", "ntl_get_timings", "ntl_stream",
-    "ntl_get_windows", "ntl_get_window_counts", "ntl_get_stages", "ntl_jit_compile_check", "ntl_pack_read", "ntl_assign_serials", "ntl_count_windows",
+    "ntl_get_windows", "ntl_get_window_counts", "ntl_get_stages", "ntl_jit_compile_check", "ntl_pack_read", "ntl_host_read_gbs", "ntl_write_read_outputs", "ntl_write_fasta_gz", "ntl_assign_serials", "ntl_count_windows",
     "ntl_reader_open", "ntl_reader_next", "ntl_reader_error", "ntl_reader_close",
 ]
 
@@ -115,6 +115,12 @@ def load() -> C.CDLL:
     L.ntl_jit_compile_check.restype = C.c_long
     L.ntl_pack_read.argtypes = [C.c_char_p, i64, i32, vp, i64, C.POINTER(i32)]
     L.ntl_pack_read.restype = C.c_long
+    L.ntl_write_read_outputs.argtypes = [vp, C.c_char_p, vp, vp, vp, vp, vp, vp, i32, i32, C.c_double, i32, i32]
+    L.ntl_write_read_outputs.restype = C.c_int
+    L.ntl_write_fasta_gz.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, i64, i32]
+    L.ntl_write_fasta_gz.restype = C.c_int
+    L.ntl_host_read_gbs.argtypes = [vp, i64, i32, i32]
+    L.ntl_host_read_gbs.restype = C.c_double
     L.ntl_assign_serials.argtypes = [vp, i32, i32, vp, vp, C.POINTER(i32)]
     L.ntl_count_windows.argtypes = [i64, i32]
     L.ntl_count_windows.restype = i32

@@ -18,7 +18,6 @@ import io
 import os
 import sys
 import time
-from concurrent.futures import ThreadPoolExecutor
 from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -280,37 +279,35 @@ def write_read_outputs(output_dir: str, reads: Sequence[Read], sc: Scanner, res:
                        order: Iterable[int], rc_applied: bool = False) -> None:
     """Per telomeric read: reads/<Serial>.fasta.gz (writeXStringSet(compress = TRUE), NanoTel.R:1870-1873) and the
     per-window tables of every track (the `subs` data frames the plot functions receive, NanoTel.R:1876-1918) as
-    density_vectors/read<Serial>.csv.  Plot rendering itself stays with the reference's R functions."""
-    rd = os.path.join(output_dir, "reads")
-    dv = os.path.join(output_dir, "density_vectors")
-    os.makedirs(rd, exist_ok=True)
-    os.makedirs(dv, exist_ok=True)
-    min_density = sc.params.min_density
-    suffixes = ("", "_mismatch", "_mismatch_tvr")[:sc.n_tracks]
-    header = ",".join(["ID", "start_index", "end_index"] + [c + sfx for sfx in suffixes for c in ("density", "class")])
-
-    def emit(s: int, name: str, seq: bytes, tables) -> None:
-        """One read's two files.  zlib releases the GIL while it compresses, so these jobs run side by side."""
-        if rc_applied:
-            seq = revcomp(seq)
-        with open(os.path.join(rd, "%d.fasta.gz" % s), "wb") as f:
-            f.write(gzip.compress(fasta_record(name, seq), 6))                               # R's gzfile() default
-        st, en = tables[0][0], tables[0][1]
-        cols = [map(str, range(1, len(st) + 1)), map(str, st.tolist()), map(str, en.tolist())]
-        for _, _, _, den in tables:
-            cls = np.where(den < min_density, np.where(den < 0.1, 0, 1), -5)                  # NanoTel.R:749-758
-            cols += [map(repr, den.tolist()), map(str, cls.tolist())]                         # repr: shortest round trip
-        with open(os.path.join(dv, "read%d.csv" % s), "w") as f:
-            f.write(header + "\n" + "\n".join(map(",".join, zip(*cols))) + "\n")
-
-    # the window tables come from the (single-threaded) context and are collected first -- once the pool runs, the
-    # main thread would wait for the GIL at every call; everything after that is per-read file work
-    order = [int(i) for i in order]
-    tables = [[sc.windows(i, t, int(res[i]["n_win"])) for t in range(sc.n_tracks)] for i in order]
-    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
-        jobs = [pool.submit(emit, int(serial[i]), reads[i][0], reads[i][1], tb) for i, tb in zip(order, tables)]
-        for j in jobs:
-            j.result()
+    density_vectors/read<Serial>.csv.  Plot rendering itself stays with the reference's R functions.
+    The files are written by the library (ntl_write_read_outputs: all host threads, zlib level 6 = R's gzfile()
+    default, doubles as shortest round-trip strings); `reads` is a reader chunk or any sequence of (name, sequence)."""
+    import ctypes as C
+    order = np.ascontiguousarray(np.asarray(list(order), dtype=np.int32))
+    if len(order) == 0:
+        os.makedirs(os.path.join(output_dir, "reads"), exist_ok=True)
+        os.makedirs(os.path.join(output_dir, "density_vectors"), exist_ok=True)
+        return
+    if isinstance(reads, _LazyChunk):
+        names, buf, off = reads.names, reads.buf, np.ascontiguousarray(reads.off, dtype=np.int64)
+    else:
+        names = [r[0] for r in reads]
+        seqs = [bytes(r[1]) for r in reads]
+        off = np.zeros(len(seqs) + 1, np.int64)
+        np.cumsum([len(x) for x in seqs], out=off[1:])
+        buf = np.frombuffer(b"".join(seqs) or b"\0", np.uint8)
+    nb = [n.encode() for n in names]
+    noff = np.zeros(len(nb) + 1, np.int64)
+    np.cumsum([len(x) for x in nb], out=noff[1:])
+    nblob = b"".join(nb) + b"\0"
+    serial = np.ascontiguousarray(serial, dtype=np.int32)
+    buf = np.ascontiguousarray(buf)
+    os.makedirs(output_dir, exist_ok=True)
+    rc_ = sc._L.ntl_write_read_outputs(sc._h, output_dir.encode(), buf.ctypes.data, off.ctypes.data, nblob,
+                                       noff.ctypes.data, serial.ctypes.data, order.ctypes.data, len(order), sc.n_tracks,
+                                       float(sc.params.min_density), int(bool(rc_applied)), os.cpu_count() or 1)
+    if rc_ != 0:
+        raise OSError("writing the per-read outputs under %s failed (ntl_write_read_outputs: %d)" % (output_dir, rc_))
 
 
 # ------------------------------------------------------------------------------------------------ chunk loop

@@ -160,6 +160,30 @@ def test_shard_bounds_cover_and_balance():
         assert max(per) - min(per) <= 2 * 250000
 
 
+def test_native_fasta_gz_writer_reproduces_the_reference_files(tmp_path):
+    """ntl_write_fasta_gz (the writer behind ntl_write_read_outputs): the reference's reads/<Serial>.fasta byte for byte
+    after gunzip; --rc frame = Biostrings::reverseComplement of the input (IUPAC letters, lower case folded)."""
+    import gzip
+    import hashlib
+    import json
+    from nanotel_b200 import _lib
+    from nanotel_b200.nanotel import fasta_record, iter_chunks, revcomp
+    L = _lib.load()
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sha = json.load(open(os.path.join(gold, "example_reads_fasta_sha256.json")))
+    (chunk,) = list(iter_chunks([os.path.join(gold, "sample.fasta")], "fasta", 10000))
+    for serial, (name, seq) in enumerate(chunk, 1):
+        path = str(tmp_path / ("%d.fasta.gz" % serial))
+        assert L.ntl_write_fasta_gz(path.encode(), name.encode(), seq, len(seq), 0) == 0
+        raw = gzip.open(path).read()
+        assert len(raw) == sha["bytes"][str(serial)] and hashlib.sha256(raw).hexdigest() == sha["sha256"][str(serial)]
+    for seq in (b"ACGTNRYKMSWBDHVacgtnrykm" * 7, b"A", b"", b"ACGT" * 40, b"ACGT" * 40 + b"C"):
+        path = str(tmp_path / "x.fasta.gz")
+        assert L.ntl_write_fasta_gz(path.encode(), b"some read  with spaces", seq, len(seq), 1) == 0
+        assert gzip.open(path).read() == fasta_record("some read  with spaces", revcomp(seq))
+    assert L.ntl_write_fasta_gz(str(tmp_path / "no_such_dir" / "x.gz").encode(), b"n", b"A", 1, 0) == -8
+
+
 def test_fasta_writer_reproduces_the_reference_files():
     """reads/<Serial>.fasta of the reference's own example run (writeXStringSet): same bytes from fasta_record()."""
     import hashlib
