@@ -328,12 +328,18 @@ def run_future_worker_chuncks(input_path: str, output_path: Optional[str], forma
                  use_filter=use_filter, right_edge=right_edge, device=device, devices=devices) as sc:
         if sc.note and verbose:
             print("note:", sc.note, file=sys.stderr)
+        tm = {"reader_wait": 0.0, "scan": 0.0, "rows": 0.0, "outputs": 0.0}
+        t_mark = time.perf_counter()
         for ci, (names, buf, soff) in enumerate(NativeReader(files, format, nrec), 1):
+            tm["reader_wait"] += time.perf_counter() - t_mark
+            t_mark = time.perf_counter()
             if verbose:
                 print(time.strftime("%Y-%m-%d %H:%M:%S"))
                 print("processing chunk", ci, "...")
             all_len.append(np.diff(soff))                                               # :2225 (before the filter)
             res = sc.scan_concat(buf, soff)
+            tm["scan"] += time.perf_counter() - t_mark
+            t_mark = time.perf_counter()
             bad = np.flatnonzero(res["status"] & _lib.READ_REF_ERROR)
             if len(bad):
                 raise RuntimeError("NanoTel.R would have stopped on read(s) %s of chunk %d (%s)" %
@@ -341,8 +347,14 @@ def run_future_worker_chuncks(input_path: str, output_path: Optional[str], forma
             serial, order, serial_start = assign_serials(res, serial_start)             # :2234-2258
             chunk = _LazyChunk(names, buf, soff)
             rows += _rows_from_results(chunk, res, serial, order, sc.n_tracks)
+            tm["rows"] += time.perf_counter() - t_mark
+            t_mark = time.perf_counter()
             if output_path:
                 write_read_outputs(output_path, chunk, sc, res, serial, order, rc_applied=do_rc)
+            tm["outputs"] += time.perf_counter() - t_mark
+            t_mark = time.perf_counter()
+        if verbose:
+            print("timing (s): " + ", ".join("%s %.2f" % kv for kv in tm.items()), file=sys.stderr)
         n_tracks = sc.n_tracks
     return {"df_summary": _frame(rows, n_tracks),
             "all_reads_length_vec": np.concatenate(all_len) if all_len else np.zeros(0, np.int64)}
