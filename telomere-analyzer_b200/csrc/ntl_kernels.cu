@@ -1190,7 +1190,13 @@ __device__ void locate_items(const ntl_read_args &a, bool valid, int r, int t, i
     }
 }
 
-__global__ void __launch_bounds__(64) ntl_locate_kernel(const ntl_read_args a)
+/* 16 CTAs of two warps per SM (64 registers, a few spilled values): with three tracks or a filtered batch there are
+ * more item groups than the 22 warps per SM of an unbounded build (92 registers) can hold in one wave -- measured:
+ * cfg3 0.143 -> 0.119 ms, cfg4 0.192 -> 0.155, cfg2 (one wave either way) unchanged */
+#ifndef NTL_LOCATE_MINB
+#define NTL_LOCATE_MINB 16
+#endif
+__global__ void __launch_bounds__(64, NTL_LOCATE_MINB) ntl_locate_kernel(const ntl_read_args a)
 {
     /* work item = (candidate read, track): the tracks of a read are independent until the keep rule;
      * cand_state[c] = {tracks done, width (or -1: error) of track 0, 1, 2} joins them.  Reads that the filter
