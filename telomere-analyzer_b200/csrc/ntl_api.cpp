@@ -507,10 +507,9 @@ int dev_pack(ntl_dev_ctx *c, const char *const *seq, const int64_t *len, int32_t
         else { h_cntoff[i] = gblocks; gblocks += round_up((len[i] + SG - 1) / SG, 8); }
     }
     c->total_blocks = spans ? c->spans2 * BPS : gblocks + 8;
-    if (spans) {
-        memset(h_fl2, NTL_SPAN_SKIP, (size_t)c->spans2);   /* alignment gaps and the rounding to whole items */
-        for (int32_t i = 0; i < n; i++) if (len[i] > 0) write_span_flags(h_fl2, first_span[i], len[i], W);
-    }
+    /* the span flags of a read (2.9 M bytes for cfg2) are written by the thread that packs it (pack_range); here only
+     * the rounding to whole items */
+    if (spans) memset(h_fl2 + sp, NTL_SPAN_SKIP, (size_t)(c->spans2 - sp));
     tr.mark("tables");
     CK(c, c->h_packed.ensure(c->arena4_off + 64));
     uint32_t *hp = (uint32_t *)((char *)c->h_packed.p + ARENA_LEAD);
@@ -537,12 +536,18 @@ int dev_pack(ntl_dev_ctx *c, const char *const *seq, const int64_t *len, int32_t
     auto pack_range = [&](int64_t b, int64_t e) {
         for (int64_t i = b; i < e; i++) {
             if (len[i] == 0) continue;
+            if (spans) {
+                write_span_flags(h_fl2, first_span[i], len[i], W);
+                const int64_t nsp = spans_of(len[i], W);
+                for (int64_t sgap = nsp; sgap < round_up(nsp, align); sgap++) h_fl2[first_span[i] + sgap] = NTL_SPAN_SKIP;   /* alignment gap */
+            }
             const int64_t nw = round_up(spans_of(len[i], W), align) * W;
             if (ntl_pack_read_2bit(seq[i], len[i], rcflag, hp + 2 * h_woff[i], nw) != 0) {
                 std::lock_guard<std::mutex> g(mu);
                 iupac.push_back((int32_t)i);
             }
         }
+        ntl_pack_fence();                       /* the packer's non-temporal stores, once per grain */
     };
     int64_t up_words = 0;                      /* position words already handed to cudaMemcpyAsync (overlap mode) */
     uint64_t packed_gen = 0;
@@ -578,8 +583,7 @@ int dev_pack(ntl_dev_ctx *c, const char *const *seq, const int64_t *len, int32_t
             }
         }
         packed_gen = c->d_packed.gen;
-        cerr = cudaMemcpyAsync(c->d_meta.p, c->h_meta.p, c->meta_bytes, cudaMemcpyHostToDevice, c->stream);
-        if (cerr == cudaSuccess) cerr = cudaMemsetAsync(c->d_packed.p, 0, ARENA_LEAD, c->stream);
+        cerr = cudaMemsetAsync(c->d_packed.p, 0, ARENA_LEAD, c->stream);
         uint32_t *dp = (uint32_t *)((char *)c->d_packed.p + ARENA_LEAD);
         const int64_t data_words = sp * W;                               /* words that the packers write */
         int64_t uf = 0;
@@ -597,6 +601,8 @@ int dev_pack(ntl_dev_ctx *c, const char *const *seq, const int64_t *len, int32_t
             else std::this_thread::yield();
         }
         for (auto &t : th) t.join();
+        /* the tables go last: the packers wrote the span flags */
+        if (cerr == cudaSuccess) cerr = cudaMemcpyAsync(c->d_meta.p, c->h_meta.p, c->meta_bytes, cudaMemcpyHostToDevice, c->stream);
         if (cerr != cudaSuccess) return fail(c, NTL_ERR_CUDA, "cudaMemcpyAsync (packed reads) failed: %s", cudaGetErrorString(cerr));
     }
     tr.mark("pack 2-bit (+copies)");
@@ -1148,7 +1154,7 @@ extern "C" long ntl_pack_read(const char *seq, int64_t len, int32_t rc, uint32_t
     const int64_t nw = (len + 31) >> 5;
     if (four_bit) *four_bit = 0;
     if (capacity < nw * 2) return NTL_ERR_NOMEM;
-    if (ntl_pack_read_2bit(seq, len, rc ? 1 : 0, words, nw) == 0) return (long)(nw * 2);
+    if (ntl_pack_read_2bit(seq, len, rc ? 1 : 0, words, nw) == 0) { ntl_pack_fence(); return (long)(nw * 2); }
     if (capacity < nw * 4) return NTL_ERR_NOMEM;
     if (ntl_pack_read_4bit(seq, len, rc ? 1 : 0, words, nw) != 0) return NTL_ERR_SEQUENCE;
     if (four_bit) *four_bit = 1;

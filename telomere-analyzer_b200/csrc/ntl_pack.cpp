@@ -98,16 +98,35 @@ static inline bool block_avx2(const char *s, int64_t L, int rc, int64_t b0, uint
 #endif
 
 #if defined(__x86_64__)
-/* 128 letters -> four position words {lo, hi} x 4 = 32 bytes per iteration, branch-free inside: four loads (byte-
+/* 128 letters -> four position words {lo, hi} x 4 = 32 bytes per iteration, branch-free inside: the letters (byte-
  * reversed for --rc), ONE validity test (c | 0x20 must equal the letter its low nibble selects: a=0x61 c=0x63 g=0x67
- * t=0x74), eight movemasks (ASCII bit 1 -> lo plane, bit 2 -> hi plane; complement = ~hi), one 32-byte store.
- * Returns the number of 128-letter groups written, or -1 if a letter is not A/C/G/T. */
+ * t=0x74; pshufb zeroes bytes >= 0x80 itself), the two planes (ASCII bit 1 -> lo, bit 2 -> hi; complement = ~hi), and
+ * four 8-byte stores {lo, hi} straight from the mask registers (a detour through a stack array costs a failed store
+ * forward per group).  Returns the number of 128-letter groups written, or -1 if a letter is not A/C/G/T.
+ * Two builds of the same loop: AVX2 (32 letters per vector, two movemasks per plane pair) and AVX-512 BW + VBMI (64
+ * letters per vector, vptestmb yields a plane of 64 positions at once, vpermb reverses the bytes): in cache 12.6 /
+ * 20 GB/s per thread for --rc against 9.4 for the round-1 loop. */
+struct PackTune { int pf_dist; bool nt; int hint; };
+#define NTL_PF2(p, hint) do { if ((hint) == 1) { _mm_prefetch((p), _MM_HINT_T1); _mm_prefetch((p) + 64, _MM_HINT_T1); } \
+    else if ((hint) == 2) { _mm_prefetch((p), _MM_HINT_T2); _mm_prefetch((p) + 64, _MM_HINT_T2); } \
+    else { _mm_prefetch((p), _MM_HINT_T0); _mm_prefetch((p) + 64, _MM_HINT_T0); } } while (0)
+static const PackTune &pack_tune()
+{
+    /* software prefetch of the input, two lines per group: the hardware streamer alone feeds one core with ~8 GB/s on
+     * the B200 hosts, 4 KiB of explicit look-ahead reach 11 GB/s (NTL_PACK_PF overrides); the packed words are written
+     * once and read next by the DMA engine: non-temporal stores save the write-allocate traffic (NTL_PACK_NT=0) */
+    static const PackTune t = {getenv("NTL_PACK_PF") ? atoi(getenv("NTL_PACK_PF")) : 4096,
+                               !(getenv("NTL_PACK_NT") && getenv("NTL_PACK_NT")[0] == '0'),
+                               getenv("NTL_PACK_HINT") ? atoi(getenv("NTL_PACK_HINT")) : 0};
+    return t;
+}
+
 template <bool RC>
 __attribute__((target("avx2")))
 static int64_t pack_groups_avx2_t(const char *s, int64_t L, uint32_t *dst, int64_t w0)
 {
-    /* the groups cover position words w0, w0 + 4, ... (w0 < 4 head words are left to the caller so that every
-     * 32-byte store of a group is aligned: a read starts at a multiple of 8 bytes, not of 32) */
+    /* the groups cover position words w0, w0 + 4, ... (w0 < 4 head words are left to the caller so that the 32 bytes
+     * of a group are aligned: a read starts at a multiple of 8 bytes, not of 32) */
     const int64_t full = (L - 32 * w0) >> 7;
     if (full <= 0) return 0;
     dst += 2 * w0;
@@ -116,14 +135,13 @@ static int64_t pack_groups_avx2_t(const char *s, int64_t L, uint32_t *dst, int64
                                          0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0);
     const __m256i rev = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0,
                                          15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
-    const __m256i m0f = _mm256_set1_epi8(0x0f), c20 = _mm256_set1_epi8(0x20);
-    /* software prefetch of the input, two lines per group: the hardware streamer alone feeds one core with ~8 GB/s on
-     * the B200 hosts, 4 KiB of explicit look-ahead reach 11 GB/s (16 threads: 87 -> 112 GB/s); NTL_PACK_PF overrides */
-    static const int pf_dist = getenv("NTL_PACK_PF") ? atoi(getenv("NTL_PACK_PF")) : 4096;
-    /* the packed words are written once and read next by the DMA engine: non-temporal stores save the
-     * write-allocate traffic; NTL_PACK_NT=0 disables */
-    static const bool nt_enabled = !(getenv("NTL_PACK_NT") && getenv("NTL_PACK_NT")[0] == '0');
-    const bool nt_store = nt_enabled && ((uintptr_t)dst & 31) == 0;
+    const __m256i c20 = _mm256_set1_epi8(0x20);
+    const int pf_dist = pack_tune().pf_dist, hint = pack_tune().hint;
+    /* non-temporal stores only for the 64-byte lines this call fills completely: a read's words start and end in the
+     * middle of a line (spans are 200 bytes), and a partially written line leaves the write-combining buffer as a
+     * string of small uncached writes; those lines take ordinary stores */
+    const bool nt_on = pack_tune().nt && ((uintptr_t)dst & 7) == 0;
+    const uintptr_t nt_lo = ((uintptr_t)dst + 63) & ~(uintptr_t)63, nt_hi = (uintptr_t)(dst + full * 8) & ~(uintptr_t)63;
     for (int64_t qq = 0; qq < full; qq++) {
         /* --rc: output group q is made of input bytes [L - 128 (q + 1), L - 128 q); the groups are produced last to
          * first so that the INPUT is read at ascending addresses (the hardware prefetchers of the host follow an
@@ -131,31 +149,73 @@ static int64_t pack_groups_avx2_t(const char *s, int64_t L, uint32_t *dst, int64
         const int64_t q = RC ? full - 1 - qq : qq;
         __m256i v[4];
         const char *b = RC ? s + (L - ((q + 1) << 7)) : s + (q << 7);
-        if (pf_dist > 0) { _mm_prefetch(b + pf_dist, _MM_HINT_T0); _mm_prefetch(b + pf_dist + 64, _MM_HINT_T0); }
+        if (pf_dist > 0) NTL_PF2(b + pf_dist, hint);
         if (!RC) {
             for (int j = 0; j < 4; j++) v[j] = _mm256_loadu_si256((const __m256i *)(b + 32 * j));
         } else {
-            for (int j = 0; j < 4; j++) {
-                __m256i x = _mm256_loadu_si256((const __m256i *)(b + 32 * (3 - j)));
-                x = _mm256_shuffle_epi8(x, rev);
-                v[j] = _mm256_permute2x128_si256(x, x, 0x01);
+            for (int j = 0; j < 4; j++) {               /* the two 16-byte halves swap places at the load */
+                const char *p = b + 32 * (3 - j);
+                const __m256i x = _mm256_inserti128_si256(_mm256_castsi128_si256(_mm_loadu_si128((const __m128i *)(p + 16))),
+                                                          _mm_loadu_si128((const __m128i *)p), 1);
+                v[j] = _mm256_shuffle_epi8(x, rev);
             }
         }
-        __m256i ok = _mm256_set1_epi8(-1);
-        for (int j = 0; j < 4; j++)
-            ok = _mm256_and_si256(ok, _mm256_cmpeq_epi8(_mm256_or_si256(v[j], c20),
-                                                        _mm256_shuffle_epi8(lut, _mm256_and_si256(v[j], m0f))));
+        __m256i ok = _mm256_cmpeq_epi8(_mm256_or_si256(v[0], c20), _mm256_shuffle_epi8(lut, v[0]));
+        for (int j = 1; j < 4; j++)
+            ok = _mm256_and_si256(ok, _mm256_cmpeq_epi8(_mm256_or_si256(v[j], c20), _mm256_shuffle_epi8(lut, v[j])));
         if (_mm256_movemask_epi8(ok) != -1) return -1;
-        alignas(32) uint32_t out[8];
+        uint64_t *o = reinterpret_cast<uint64_t *>(dst + q * 8);
+        const bool nt_store = nt_on && (uintptr_t)o >= nt_lo && (uintptr_t)o + 32 <= nt_hi;
         for (int j = 0; j < 4; j++) {
-            out[2 * j] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v[j], 6));        /* ASCII bit 1 -> code bit 0 */
-            const uint32_t h = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v[j], 5));  /* ASCII bit 2 -> code bit 1 */
-            out[2 * j + 1] = RC ? ~h : h;
+            const uint64_t l = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v[j], 6));   /* ASCII bit 1 -> code bit 0 */
+            const uint64_t h = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v[j], 5));   /* ASCII bit 2 -> code bit 1 */
+            uint64_t w = l | (h << 32);
+            if (RC) w ^= 0xffffffff00000000ull;
+            if (nt_store) _mm_stream_si64(reinterpret_cast<long long *>(o + j), (long long)w);
+            else memcpy(o + j, &w, 8);
         }
-        if (nt_store) _mm256_stream_si256((__m256i *)(dst + q * 8), _mm256_load_si256((const __m256i *)out));
-        else memcpy(dst + q * 8, out, 32);
     }
-    if (nt_store) _mm_sfence();
+    return full;
+}
+
+template <bool RC>
+__attribute__((target("avx512f,avx512bw,avx512vbmi")))
+static int64_t pack_groups_avx512_t(const char *s, int64_t L, uint32_t *dst, int64_t w0)
+{
+    const int64_t full = (L - 32 * w0) >> 7;
+    if (full <= 0) return 0;
+    dst += 2 * w0;
+    if (RC) L -= 32 * w0; else s += 32 * w0;
+    const __m512i bit1 = _mm512_set1_epi8(2), bit2 = _mm512_set1_epi8(4), c20 = _mm512_set1_epi8(0x20);
+    const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0));
+    alignas(64) static const uint8_t revidx[64] = {
+        63, 62, 61, 60, 59, 58, 57, 56, 55, 54, 53, 52, 51, 50, 49, 48, 47, 46, 45, 44, 43, 42, 41, 40, 39, 38, 37, 36, 35, 34, 33, 32,
+        31, 30, 29, 28, 27, 26, 25, 24, 23, 22, 21, 20, 19, 18, 17, 16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0};
+    const __m512i rev = _mm512_load_si512(revidx);
+    const int pf_dist = pack_tune().pf_dist, hint = pack_tune().hint;
+    const bool nt_on = pack_tune().nt && ((uintptr_t)dst & 7) == 0;     /* whole lines only, see above */
+    const uintptr_t nt_lo = ((uintptr_t)dst + 63) & ~(uintptr_t)63, nt_hi = (uintptr_t)(dst + full * 8) & ~(uintptr_t)63;
+    for (int64_t qq = 0; qq < full; qq++) {
+        const int64_t q = RC ? full - 1 - qq : qq;      /* --rc: input read at ascending addresses, see above */
+        const char *b = RC ? s + (L - ((q + 1) << 7)) : s + (q << 7);
+        if (pf_dist > 0) NTL_PF2(b + pf_dist, hint);
+        __m512i v0, v1;
+        if (!RC) { v0 = _mm512_loadu_si512(b); v1 = _mm512_loadu_si512(b + 64); }
+        else { v0 = _mm512_permutexvar_epi8(rev, _mm512_loadu_si512(b + 64)); v1 = _mm512_permutexvar_epi8(rev, _mm512_loadu_si512(b)); }
+        const __mmask64 k0 = _mm512_cmpeq_epi8_mask(_mm512_or_si512(v0, c20), _mm512_shuffle_epi8(lut, v0));
+        const __mmask64 k1 = _mm512_cmpeq_epi8_mask(_mm512_or_si512(v1, c20), _mm512_shuffle_epi8(lut, v1));
+        if ((k0 & k1) != ~0ull) return -1;
+        /* a plane of 64 positions per test: l = {lo of word 2i | lo of word 2i + 1 << 32} */
+        const uint64_t l0 = _mm512_test_epi8_mask(v0, bit1), l1 = _mm512_test_epi8_mask(v1, bit1);
+        uint64_t h0 = _mm512_test_epi8_mask(v0, bit2), h1 = _mm512_test_epi8_mask(v1, bit2);
+        if (RC) { h0 = ~h0; h1 = ~h1; }
+        const uint64_t w[4] = {(l0 & 0xffffffffu) | (h0 << 32), (l0 >> 32) | (h0 & 0xffffffff00000000ull),
+                               (l1 & 0xffffffffu) | (h1 << 32), (l1 >> 32) | (h1 & 0xffffffff00000000ull)};
+        uint64_t *o = reinterpret_cast<uint64_t *>(dst + q * 8);
+        const bool nt_store = nt_on && (uintptr_t)o >= nt_lo && (uintptr_t)o + 32 <= nt_hi;
+        if (nt_store) for (int j = 0; j < 4; j++) _mm_stream_si64(reinterpret_cast<long long *>(o + j), (long long)w[j]);
+        else memcpy(o, w, 32);
+    }
     return full;
 }
 #endif
@@ -166,6 +226,24 @@ static bool g_have_avx2 =
 #else
     false;
 #endif
+/* NTL_PACK_ISA=avx2 keeps the 256-bit loop on a host that has AVX-512 (measurements) */
+static bool g_have_avx512 =
+#if defined(__x86_64__)
+    __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi") &&
+    !(getenv("NTL_PACK_ISA") && strcmp(getenv("NTL_PACK_ISA"), "avx2") == 0);
+#else
+    false;
+#endif
+
+/* The group loops write with non-temporal stores and do NOT fence: a fence per read drains the write-combining
+ * buffers every 20 kb and cost ~0.4 us per read; the caller issues ntl_pack_fence() once per batch of reads, before
+ * anyone else (the DMA engine, another thread) is told that the words are there. */
+void ntl_pack_fence(void)
+{
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
+}
 
 int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst, int64_t n_words)
 {
@@ -173,13 +251,19 @@ int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst, int64_t 
     const int64_t n_blocks = (L + 31) >> 5;          /* position words that hold letters */
     int64_t k = 0, k_skip_lo = 0, k_skip_hi = 0;     /* words [k_skip_lo, k_skip_hi) were written by the vector loop */
 #if defined(__x86_64__)
-    if (g_have_avx2) {
-        const int64_t w0 = ((uintptr_t)dst & 7) == 0 ? (int64_t)(((32 - ((uintptr_t)dst & 31)) & 31) >> 3) : 0;
-        const int64_t full = rc ? pack_groups_avx2_t<true>(s, L, dst, w0) : pack_groups_avx2_t<false>(s, L, dst, w0);
+    if (g_have_avx2 && ((uintptr_t)dst & 7) == 0) {
+        /* whole groups of 128 letters from word 0 on (8-byte stores: no alignment beyond the read's own) */
+        /* the groups start at the first 32-byte boundary of the output (w0 <= 3 head words are left to the loop below):
+         * a group's four 8-byte stores then never straddle a line (measured on the B200 hosts, 16 threads: 124 against
+         * 114 GB/s for 20 kb reads, 61 against 34 GB/s for 2 kb reads) */
+        const int64_t w0 = (int64_t)(((32 - ((uintptr_t)dst & 31)) & 31) >> 3);
+        const int64_t full = g_have_avx512 ? (rc ? pack_groups_avx512_t<true>(s, L, dst, w0) : pack_groups_avx512_t<false>(s, L, dst, w0))
+                                           : (rc ? pack_groups_avx2_t<true>(s, L, dst, w0) : pack_groups_avx2_t<false>(s, L, dst, w0));
         if (full < 0) return 1;
         if (full > 0) { k_skip_lo = w0; k_skip_hi = w0 + (full << 2); }
     }
 #endif
+    /* at most three whole words at either end and one partial word are left */
     for (; k < n_blocks; k++) {
         if (k == k_skip_lo && k_skip_hi > k_skip_lo) { k = k_skip_hi - 1; continue; }
         uint32_t lo, hi;
@@ -187,8 +271,19 @@ int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst, int64_t 
         const int n = L - b0 >= 32 ? 32 : (int)(L - b0);
         bool ok;
 #if defined(__x86_64__)
-        if (n == 32 && g_have_avx2) ok = block_avx2(s, L, rc, b0, &lo, &hi);
-        else
+        if (g_have_avx2) {
+            if (n == 32) ok = block_avx2(s, L, rc, b0, &lo, &hi);
+            else {
+                /* the partial word through the same vector code: its n letters in a 32-byte buffer padded with 'A'
+                 * (forward: at the front; --rc: at the back, the block is the reversal of the read's first n letters) */
+                char tmp[32];
+                memset(tmp, 'A', 32);
+                if (rc) memcpy(tmp + 32 - n, s, (size_t)n); else memcpy(tmp, s + b0, (size_t)n);
+                ok = block_avx2(tmp, 32, rc, 0, &lo, &hi);
+                const uint32_t m = (1u << n) - 1u;
+                lo &= m; hi &= m;
+            }
+        } else
 #endif
             ok = block_scalar(s, L, rc, b0, n, &lo, &hi);
         if (!ok) return 1;

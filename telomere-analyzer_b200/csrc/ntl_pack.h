@@ -9,6 +9,9 @@
  * rc != 0: write the reverse complement.  Returns 0, or 1 if the read has a letter other than A/C/G/T (any case);
  * the caller then re-packs it with ntl_pack_read_4bit. */
 int ntl_pack_read_2bit(const char *s, int64_t L, int rc, uint32_t *dst, int64_t n_words);
+/* ntl_pack_read_2bit writes with non-temporal stores and does not fence: call this once after a batch of reads,
+ * before another agent (DMA engine, another thread) is told that the words are in memory. */
+void ntl_pack_fence(void);
 /* 4-bit position words {A, C, G, T} (Biostrings code bits; gap letters have none), 16 bytes per 32 positions.
  * Returns 0, or -1 if a letter is outside the Biostrings DNA alphabet. */
 int ntl_pack_read_4bit(const char *s, int64_t L, int rc, uint32_t *dst, int64_t n_words);
