@@ -58,6 +58,15 @@ def test_packer_matches_layout(rc):
         exp, efb = _expected(seq, rc)
         assert not fb and not efb
         assert np.array_equal(got, exp), (L, rc)
+    # every 8-byte alignment of the output inside a 32-byte block (the vector loop starts at the first 32-byte boundary
+    # and leaves 0-3 head words and 0-3 tail words + a partial word to the block code), lengths around every hand-over
+    for mis in (0, 2, 4, 6):
+        for L in list(range(120, 140)) + list(range(155, 165)) + list(range(250, 262)) + list(range(284, 292)) + \
+                list(range(380, 390)) + list(range(509, 518)) + [1000, 4095, 4096, 4097, 4099, 4127, 4128, 4129]:
+            seq = bytes(rng.choice(np.frombuffer(b"ACGTacgt", np.uint8), L))
+            got, fb = _pack(seq, rc, misalign=mis)
+            exp, efb = _expected(seq, rc)
+            assert not fb and not efb and np.array_equal(got, exp), (L, rc, mis)
     for L in (1, 5, 33, 128, 129, 700):
         seq = bytearray(rng.choice(np.frombuffer(b"ACGT", np.uint8), L))
         seq[int(rng.integers(0, L))] = ord("N")
