@@ -334,6 +334,7 @@ struct WinTab {                 /* the window table of one track (analyze_subtel
     const uint16_t *cnt;        /* covered bases per block of SG positions (K2); window k = blocks k Q .. k Q + Q - 1, */
     int n, nb, Q, SG, S, L;     /* the last window = every remaining block (n windows, nb blocks)                     */
     int thr_reg, thr_last;      /* smallest telomeric count of a regular window / of this read's last window */
+    const double *dens;         /* dens[c] = (double)c / (double)S: the density of a regular window (host table)       */
     const u32 *cls;             /* the track's class-bit plane (ntl_dev.h) as 32-bit words                            */
     long long bit0;             /* bit address of the read's block 0                                                  */
     int bps;                    /* blocks per class byte                                                              */
@@ -414,7 +415,9 @@ __device__ __forceinline__ bool wt_telo_count(const WinTab &w, int k, int count)
 }
 __device__ __forceinline__ double wt_density_of_count(const WinTab &w, int k, int count)
 {
-    /* get_sub_density (NanoTel.R:467): count / width in double */
+    /* get_sub_density (NanoTel.R:467): count / width in double; a regular window has width S, and count / S comes
+     * from the table the host filled with that same IEEE division (a cached load instead of ~80 instructions) */
+    if (k < w.n - 1) return __ldg(w.dens + count);
     return k3_div((double)count, (double)(wt_end(w, k) - wt_start(w, k) + 1));
 }
 
@@ -482,7 +485,10 @@ __device__ __noinline__ void find_telo_position(const WinTab &w, double R, doubl
     int end_position = 0;                                                /* 1-based i + 1 (:1022) */
     WinBuf wb;
     wb.base = 0; wb.dir = 0; wb.c = 0; wb.d = 0.0;
-    for (int k = 0; k < n;) {                                            /* :1003-1025 */
+    /* leading non-telomeric windows only reset a state that is still the initial one: start at the first telomeric
+     * window (with the reference's R >= 3 the degenerate exit below cannot fire on them) */
+    const bool jump = R > 0.0 || T > 0.0;
+    for (int k = jump ? next_telo_fwd(w, 0, sub, tmask, lane) : 0; k < n;) {        /* :1003-1025 */
         int c; double dk;
         wb_get(wb, w, k, 1, sub, tmask, &c, &dk);
         if (!wt_telo_count(w, k, c)) {
@@ -505,7 +511,8 @@ __device__ __noinline__ void find_telo_position(const WinTab &w, double R, doubl
         if (i < end_position) i = end_position;
         end = wt_end(w, (i < n ? i : n) - 1);                            /* end_position may be n + 1: the loop does not run */
     } else {                                                             /* :1046-1068 */
-        for (int i = n; i >= end_position;) {
+        /* the same from the other end: trailing non-telomeric windows only reset the initial state */
+        for (int i = next_telo_bwd(w, n - 1, sub, tmask, lane) + 1; i >= end_position;) {
             int c; double dk;
             wb_get(wb, w, i - 1, -1, sub, tmask, &c, &dk);
             if (!wt_telo_count(w, i - 1, c)) {
@@ -1067,7 +1074,7 @@ __device__ void locate_items(const ntl_read_args &a, bool valid, int r, int t, i
     WinTab w;
     rv.L = 0; rv.fmt = 0; rv.base = nullptr; rv.n_words = 0; rv.n_raw = 0; rv.ccov = nullptr; rv.cwb = nullptr;
     w.cnt = nullptr; w.n = 0; w.nb = 0; w.Q = 1; w.SG = 1; w.S = 1; w.L = 0; w.thr_reg = 0; w.thr_last = 0;
-    w.cls = nullptr; w.bit0 = 0; w.bps = 8;
+    w.cls = nullptr; w.bit0 = 0; w.bps = 8; w.dens = nullptr;
     const int S = c_prm.S, T = c_prm.n_tracks;
     int n_win = 0, status = 0;
     ntl_track out;
@@ -1089,7 +1096,7 @@ __device__ void locate_items(const ntl_read_args &a, bool valid, int r, int t, i
         if (n_win <= 0) status |= NTL_READ_NO_WINDOWS;
         w.cnt = a.cnt[t] + a.cnt_off[r]; w.n = n_win > 0 ? n_win : 0; w.S = S; w.L = rv.L;
         w.Q = c_prm.Q; w.SG = c_prm.SG; w.nb = (rv.L + c_prm.SG - 1) / c_prm.SG;
-        w.thr_reg = c_prm.thr_reg;
+        w.thr_reg = c_prm.thr_reg; w.dens = a.dens;
         w.cls = reinterpret_cast<const u32 *>(a.cls[t]); w.bps = c_prm.cls_bps; w.bit0 = c_prm.cls_bps == 8 ? a.cnt_off[r] : a.cnt_off[r] / c_prm.cls_bps * 8;
         w.thr_last = w.n > 0 ? (int)a.thr[wt_end(w, w.n - 1) - wt_start(w, w.n - 1) + 1] : 0;
     }

@@ -28,24 +28,31 @@ ap.add_argument("--devices", default=None)
 ap.add_argument("--no-filter", action="store_true")
 a = ap.parse_args()
 
-buf, off, meta = synth_reads(a.reads, 20261018 + 4, telomeric_frac=0.30)
 d = tempfile.mkdtemp(prefix="ntl_cli_")
 fq = os.path.join(d, "in")                              # -i takes a file or a directory of files
 os.makedirs(fq)
-
-
-def write_part(j):
-    with gzip.open(os.path.join(fq, "part%03d.fastq.gz" % j), "wb", compresslevel=1) as f:
-        for i in range(j * a.reads // a.files, (j + 1) * a.reads // a.files):
-            s = buf[int(off[i]):int(off[i + 1])].tobytes()
-            f.write(b"@read%08d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")
-
-
+# the input is generated in blocks of at most 100 000 reads (own seed each, a.files files per block) so that a
+# 1 000 000-read run (BASELINE.json configs[3]) never holds more than one block of ASCII in memory
+BLOCK = 100000
 t0 = time.perf_counter()
-with ThreadPoolExecutor(max_workers=min(a.files, os.cpu_count() or 1)) as pool:
-    list(pool.map(write_part, range(a.files)))
+total_bases = 0
+for blk in range((a.reads + BLOCK - 1) // BLOCK):
+    nb = min(BLOCK, a.reads - blk * BLOCK)
+    buf, off, meta = synth_reads(nb, 20261018 + 4 + 1000 * blk, telomeric_frac=0.30)
+    total_bases += int(meta["bases"])
+
+    def write_part(j, blk=blk, nb=nb, buf=buf, off=off):
+        with gzip.open(os.path.join(fq, "part%03d_%03d.fastq.gz" % (blk, j)), "wb", compresslevel=1) as f:
+            for i in range(j * nb // a.files, (j + 1) * nb // a.files):
+                s = buf[int(off[i]):int(off[i + 1])].tobytes()
+                f.write(b"@read%08d\n" % (blk * BLOCK + i) + s + b"\n+\n" + b"I" * len(s) + b"\n")
+
+    with ThreadPoolExecutor(max_workers=min(a.files, os.cpu_count() or 1)) as pool:
+        list(pool.map(write_part, range(a.files)))
+    del buf, off
+meta = {"bases": total_bases}
 gz_bytes = sum(os.path.getsize(os.path.join(fq, f)) for f in os.listdir(fq))
-print(json.dumps({"generated": a.files, "gz_bytes": gz_bytes, "seconds": round(time.perf_counter() - t0, 1)}), flush=True)
+print(json.dumps({"generated": len(os.listdir(fq)), "gz_bytes": gz_bytes, "seconds": round(time.perf_counter() - t0, 1)}), flush=True)
 env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "telomere-analyzer_b200"))
 run = 0
 for S in a.S:
