@@ -6,7 +6,8 @@
  *                                      class per track
  * for every summary row of a chunk.  The command-line driver spent most of its wall clock formatting these files in
  * Python; here one call writes them with all host threads (zlib level 6 = R's gzfile() default; doubles as the
- * shortest decimal string that reads back to the same value, the form readr::write_csv prints).
+ * shortest decimal string that reads back to the same value, integral values without a decimal point: the form
+ * readr::write_csv prints).
  * Plot rendering stays with the reference's own R functions (R/plot_density_vectors.R).
  */
 #include "../../include/nanotel_b200.h"
@@ -77,15 +78,12 @@ bool gzip_to_file(const std::string &text, const char *path, int level, std::vec
     return fclose(f) == 0 && ok;
 }
 
-/* the shortest decimal string that round-trips, with ".0" for integral values (Python's repr / readr's doubles) */
+/* the shortest decimal string that round-trips, integral values without a decimal point: readr::write_csv's doubles */
 void append_double(std::string &s, double x)
 {
     char b[40];
     auto r = std::to_chars(b, b + sizeof b, x);
-    bool plain = true;
-    for (char *p = b; p < r.ptr; p++) if (*p == '.' || *p == 'e' || *p == 'n' || *p == 'i') plain = false;
     s.append(b, (size_t)(r.ptr - b));
-    if (plain) s.append(".0");
 }
 void append_int(std::string &s, long long v)
 {

@@ -246,8 +246,16 @@ def revcomp(seq: bytes) -> bytes:
 
 
 # ------------------------------------------------------------------------------------------------ outputs
-def _fmt_double(x: float) -> str:
-    return repr(float(x))            # shortest round-trip representation, as readr::write_csv prints doubles
+def fmt_double(x: float) -> str:
+    """A double as readr::write_csv prints it: the shortest decimal string that reads back to the same value, and no
+    decimal point for integral values (1 -> "1", 0 -> "0")."""
+    x = float(x)
+    if x == int(x) and abs(x) < 1e15:
+        return str(int(x))
+    return repr(x)
+
+
+_fmt_double = fmt_double
 
 
 def write_summary_csv(df, path: str) -> None:
@@ -377,12 +385,61 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--tvr_patterns", default=None)
     ap.add_argument("--version", action="store_true", default=False)
     ap.add_argument("--analysis", action="store_true", default=False,
-                    help="post-processing of the reference (NanoTel.R:2438-2508) -- not part of the CUDA path")
+                    help="post-processing of the reference (NanoTel.R:2438-2508): filtered, sorted summary + results.txt")
     ap.add_argument("--device", type=int, default=0, help="CUDA device ordinal (extension)")
     ap.add_argument("--devices", default=None,
                     help='space or comma separated CUDA ordinals, or "all": every --nrec chunk is sharded over them '
                          "(extension; replaces the 8 forked workers of NanoTel.R:2207)")
     return ap
+
+
+def _r_number(x) -> str:
+    """paste0(<numeric>) of R: up to 15 significant digits, no trailing zeros; NA / NaN as R prints them."""
+    if x is None:
+        return "NA"
+    x = float(x)
+    if x != x:
+        return "NaN"
+    return fmt_double(float("%.15g" % x))
+
+
+def run_analysis(df, save_path: str, barcode_name: str):
+    """The --analysis post-processing of NanoTel.R:2438-2508 (host side, no GPU): keep rows with telo_density_mismatch
+    >= 0.75 and Telomere_start_mismatch <= 134, sort by sequence_length (longest first, ties in row order), add the
+    running median of Telomere_length_mismatch and sequence_length minus it, drop rows where that difference is below
+    134; writes <barcode>_filtered_sorted_summary.csv and <barcode>_results.txt.  The reference also draws
+    <barcode>_telomere_plot.png with ggplot; here the three curves of that plot are written as
+    <barcode>_telomere_plot_data.csv (read_index, sequence_length, Telomere_length_mismatch, TelLenMM_RunningMed).
+    Returns (df_filtered, df_for_plot)."""
+    import bisect
+    import pandas as pd
+    keep = (df["telo_density_mismatch"].astype("float64") >= 0.75) & (df["Telomere_start_mismatch"].astype("float64") <= 134)
+    d = df[keep.fillna(False)].copy()                                                    # NA comparisons drop the row
+    d = d.iloc[np.argsort(-d["sequence_length"].to_numpy(dtype=np.int64), kind="stable")].reset_index(drop=True)
+    run_med, sorted_vals = [], []
+    for v in d["Telomere_length_mismatch"].to_numpy(dtype=np.float64):
+        bisect.insort(sorted_vals, float(v))
+        m = len(sorted_vals)
+        run_med.append(sorted_vals[m // 2] if m % 2 else 0.5 * (sorted_vals[m // 2 - 1] + sorted_vals[m // 2]))
+    d["TelLenMM_RunningMed"] = np.array(run_med, dtype=np.float64)
+    d["SeqLen_minus_RunMed"] = d["sequence_length"].to_numpy(dtype=np.float64) - d["TelLenMM_RunningMed"].to_numpy()
+    df_for_plot = d.copy()
+    df_for_plot["read_index"] = np.arange(1, len(d) + 1, dtype=np.int64)
+    d = d[d["SeqLen_minus_RunMed"] >= 134].reset_index(drop=True)
+    write_summary_csv(d, os.path.join(save_path, barcode_name + "_filtered_sorted_summary.csv"))
+    n_reads = len(d)
+    tl = d["Telomere_length_mismatch"].to_numpy(dtype=np.float64)
+    med_telo = float(np.median(tl)) if n_reads else None
+    pct_short = round(100.0 * float((tl < 2000).sum()) / n_reads, 1) if n_reads else float("nan")
+    with open(os.path.join(save_path, barcode_name + "_results.txt"), "w") as f:
+        f.write("Results for %s\n" % barcode_name)
+        f.write("==========================================\n")
+        f.write("Number of telomeric reads after filtration : %d\n" % n_reads)
+        f.write("Median telomere length with mismatch (bp)  : %s\n" % _r_number(med_telo))
+        f.write("%% of telomeres shorter than 2kb            : %s%%\n" % _r_number(pct_short))
+    write_summary_csv(df_for_plot[["read_index", "sequence_length", "Telomere_length_mismatch", "TelLenMM_RunningMed"]],
+                      os.path.join(save_path, barcode_name + "_telomere_plot_data.csv"))
+    return d, df_for_plot
 
 
 def main(argv: Optional[Sequence[str]] = None) -> int:
@@ -428,8 +485,7 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
             f.write("%% of total reads: %s%%\n" % round(100.0 * len(df) / len(lens), 2))
         f.write("Elapsed: %.3f s\n" % (time.time() - t1))
     if opt.analysis:
-        print("--analysis is the reference's downstream post-processing (NanoTel.R:2438-2508); it is outside the "
-              "CUDA hot path and not implemented here", file=sys.stderr)
+        run_analysis(df, opt.save_path, barcode_name)
     return 0
 
 

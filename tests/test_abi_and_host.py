@@ -196,3 +196,57 @@ def test_fasta_writer_reproduces_the_reference_files():
     for serial, (name, seq) in enumerate(chunk, 1):
         raw = fasta_record(name, seq)
         assert len(raw) == sha["bytes"][str(serial)] and hashlib.sha256(raw).hexdigest() == sha["sha256"][str(serial)]
+
+
+def test_fmt_double_is_readr_style():
+    from nanotel_b200.nanotel import fmt_double
+    assert fmt_double(1.0) == "1" and fmt_double(0.0) == "0" and fmt_double(0.5) == "0.5"
+    assert fmt_double(0.9919354838709677) == "0.9919354838709677" and fmt_double(8 / 21) == repr(8 / 21)
+    assert fmt_double(1234.5) == "1234.5" and fmt_double(2981.0) == "2981"
+
+
+def test_analysis_post_processing(tmp_path):
+    """--analysis (NanoTel.R:2438-2508): filter, sort, running median, second filter, the two output files --
+    against a literal restatement of the R pipeline on a table with NA rows, ties and both filters biting."""
+    import csv
+    import statistics
+    from nanotel_b200.nanotel import _frame, run_analysis
+    rng = np.random.default_rng(4)
+    rows = []
+    for i in range(240):
+        L = int(rng.choice([1200, 2000, 3000, 5000, 5000, 8000, 12000, 20000]))   # ties in sequence_length
+        tl = int(rng.integers(200, min(L, 9000)))
+        dens_mm = float(rng.choice([0.5, 0.74, 0.75, 0.8, 0.97, 1.0]))
+        st_mm = int(rng.choice([1, 20, 134, 135, 400]))
+        row = [i + 1, "read%02d extra" % i, L, 0.9, 1, tl, tl, dens_mm, st_mm, st_mm + tl - 1, tl]
+        if i % 11 == 0:
+            row[7:11] = [None, None, None, None]                               # NA on the mismatch track
+        rows.append(row)
+    df = _frame(rows, 2)
+    got, for_plot = run_analysis(df, str(tmp_path), "bc01")
+    # R: filter -> arrange(desc(sequence_length)) (stable) -> running median -> filter
+    kept = [r for r in rows if r[7] is not None and r[7] >= 0.75 and r[8] <= 134]
+    kept.sort(key=lambda r: -r[2])
+    exp = []
+    for i, r in enumerate(kept):
+        med = statistics.median([x[10] for x in kept[:i + 1]])
+        exp.append((r[0], r[2], r[10], float(med), r[2] - float(med)))
+    assert [tuple(x) for x in for_plot[["Serial", "sequence_length", "Telomere_length_mismatch", "TelLenMM_RunningMed",
+                                        "SeqLen_minus_RunMed"]].itertuples(index=False)] == exp
+    assert for_plot["read_index"].tolist() == list(range(1, len(exp) + 1))
+    final = [e for e in exp if e[4] >= 134]
+    assert 0 < len(final) < len(exp) < len(rows)
+    assert got["Serial"].tolist() == [e[0] for e in final]
+    out = list(csv.reader(open(tmp_path / "bc01_filtered_sorted_summary.csv")))
+    assert out[0][-2:] == ["TelLenMM_RunningMed", "SeqLen_minus_RunMed"] and len(out) == len(final) + 1
+    assert [r[0] for r in out[1:]] == [str(e[0]) for e in final]
+    txt = open(tmp_path / "bc01_results.txt").read().split("\n")
+    assert txt[0] == "Results for bc01" and txt[2].endswith(": %d" % len(final))
+    med = statistics.median([e[2] for e in final])
+    assert txt[3].endswith(": " + (str(int(med)) if med == int(med) else repr(float(med))))
+    pct = round(100.0 * sum(e[2] < 2000 for e in final) / len(final), 1)
+    assert txt[4].endswith(": " + (str(int(pct)) if pct == int(pct) else repr(pct)) + "%")
+    assert len(list(csv.reader(open(tmp_path / "bc01_telomere_plot_data.csv")))) == len(exp) + 1
+    # nothing survives: R prints NA and NaN
+    got0, _ = run_analysis(df.iloc[:0], str(tmp_path), "empty")
+    assert len(got0) == 0 and "NA" in open(tmp_path / "empty_results.txt").read()

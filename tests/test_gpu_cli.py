@@ -9,6 +9,7 @@ import os
 import numpy as np
 import pytest
 
+from nanotel_b200.nanotel import fmt_double
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -33,7 +34,7 @@ def _expected_rows(chunks, patterns, tvr, min_density, S, right_edge, rc, use_fi
                 if int(tr["start"]) == -1:
                     row += ["NA"] * 4
                 else:
-                    row += [repr(float(tr["density"])), str(int(tr["start"])), str(int(tr["end"])),
+                    row += [fmt_double(float(tr["density"])), str(int(tr["start"])), str(int(tr["end"])),
                             str(int(tr["end"]) - int(tr["start"]) + 1)]
             rows.append(row)
     return rows
@@ -61,8 +62,8 @@ def test_cli_on_the_reference_example(tmp_path):
         res = O.analyze_read(O.make_params("TTAGGG"), seq)
         st, en = O.split_telo(len(seq), 100)
         assert [int(r["start_index"]) for r in dv] == st.tolist()
-        assert [r["density"] for r in dv] == [repr(float(c) / float(w)) for c, w in zip(res.win_counts[0], en - st + 1)]
-        assert [r["density_mismatch"] for r in dv] == [repr(float(c) / float(w)) for c, w in zip(res.win_counts[1], en - st + 1)]
+        assert [r["density"] for r in dv] == [fmt_double(float(c) / float(w)) for c, w in zip(res.win_counts[0], en - st + 1)]
+        assert [r["density_mismatch"] for r in dv] == [fmt_double(float(c) / float(w)) for c, w in zip(res.win_counts[1], en - st + 1)]
 
 
 def test_cli_chunked_rc_filter_tvr_serials(tmp_path):
