@@ -8,7 +8,7 @@
  *       ntl_items_kernel       compacts the marked work items into the list the span scan walks
  *   K3a ntl_triage_kernel      one thread per read: proves that a read has no telomeric window on any track and no
  *                              hit in its first 18 bases and writes its (trivial) record, or hands it to K3b
- *   K3b ntl_locate_kernel      one warp per (candidate read, track): locator and refinement (find_telo_position_wraper
+ *   K3b ntl_locate_kernel      a team of eight lanes per (candidate read, track): locator and refinement (find_telo_position_wraper
  *                              NanoTel.R:1080-1155 and everything it calls, analyze_read's densities and keep rule
  *                              :1840-1868)
  *       ntl_gather_windows_kernel   block counts of the kept reads, packed for the device-to-host copy
@@ -321,11 +321,14 @@ __global__ void __launch_bounds__(256) ntl_items_kernel(const uint8_t *active, i
 }
 
 /* =============================================================================================================
- * K3: locator.  ONE THREAD per (candidate read, track): the window state machines of the reference are sequential
- * scans with data-dependent exits, and a candidate needs only a few hundred bases of locally recomputed coverage, so
- * a warp per item spends its 32 lanes on the same scalar work (measured: 4 300 warp-instructions per item, 41 % issue
- * utilisation, bound by dependent latency); per thread the same item is a few thousand scalar instructions, 32 items
- * share every warp-instruction, and the lanes of a warp (neighbouring tracks of the same reads) follow similar paths.
+ * K3: locator.  The window state machines of the reference are sequential scans with data-dependent exits, and a
+ * candidate needs only a few hundred bases of locally recomputed coverage.  Measured over two rounds: a warp per
+ * (read, track) item spends its 32 lanes on the same scalar work (4 300 warp-instructions per item, 41 % issue
+ * utilisation, bound by dependent latency); one thread per item divides the instruction count by 32 but leaves every
+ * load -> divide -> compare chain fully exposed.  The kernel below gives an item a TEAM of eight lanes: the state
+ * machines run on all eight alike, and everything that has data parallelism in it is spread over them -- the class-bit
+ * searches (512 windows per step), the window counts and their densities (eight windows per load and division), the
+ * coverage words recomputed from the read (one per lane), the whole-block sums.
  * ============================================================================================================= */
 /* one copy of the IEEE double division (a ~80-instruction sequence) for the whole locate kernel */
 __device__ __noinline__ double k3_div(double a, double b) { return a / b; }
@@ -931,7 +934,7 @@ __device__ __noinline__ void search_both(const ReadView &rv, bool doR, int end_i
  * window lies beyond max_diff = 200 of the chosen edge (:861, :921), search_right_patterns looks at s[1..18]
  * (:1141 with end_index 0) and, finding nothing, leaves (-1, 0): width 2 < 30, not telomeric (:1847).  The thread
  * verifies each of those conditions (integer window classes, one bit-parallel match over the first word) and writes
- * the record; every other read goes on the candidate list of the warp-per-read locate kernel.
+ * the record; every other read goes on the candidate list of the locate kernel.
  * ============================================================================================================= */
 __device__ __forceinline__ bool triage_first_window_hit(u32 lo, u32 hi, int T)
 {
@@ -1061,8 +1064,8 @@ __global__ void __launch_bounds__(128) ntl_triage_kernel(const ntl_read_args a)
 }
 
 /* =============================================================================================================
- * K3b: full locator, one THREAD per (candidate read, track); the thread that completes a read's last track writes
- * the record head.
+ * K3b: full locator, a team of eight lanes per (candidate read, track); the team that completes a read's last track
+ * writes the record head.
  * ============================================================================================================= */
 /* One item per team, four teams per warp.  The four items of a warp are walked in PHASES with a warp barrier between
  * them: inside a phase the teams run the same code (the coverage recomputation has fixed trip counts), and teams that
