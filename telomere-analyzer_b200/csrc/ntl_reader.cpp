@@ -11,6 +11,10 @@
  * of the parser each have their own thread that inflates AND parses the file into a bounded queue of record batches
  * (a nanopore run is thousands of small fastq.gz files; one gzip stream cannot be inflated in parallel, a list of
  * them can); the consumer only concatenates batches into --nrec chunks.
+ * A file in BGZF form (bgzip / htslib: a chain of gzip members of <= 64 KiB, each announcing its compressed size in a
+ * "BC" extra field) CAN be inflated in parallel: when fewer files than cores are open, such a file gets a pool of
+ * inflate threads of its own (BgzfSource below: blocks are read sequentially, inflated in groups by the pool, handed
+ * to the line parser in order).  Plain single-member gzip has no such seams and stays on one thread (zlib's gzread).
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -39,6 +43,145 @@ struct Batch {
     void close_record() { seq_end.push_back((int64_t)seq.size()); name_end.push_back((int64_t)names.size()); n++; }
 };
 
+/* A BGZF file inflated by a pool of threads.  The owner (the file's producer thread) reads the compressed blocks in
+ * order and groups ~1 MiB of them into a job; the pool inflates jobs (raw deflate per block, CRC32 checked); next()
+ * hands out the decompressed bytes of the jobs in file order. */
+struct BgzfSource {
+    struct Job {
+        std::vector<unsigned char> raw;                 /* the blocks' deflate data, back to back */
+        std::vector<uint32_t> clen, isize, crc;         /* per block */
+        std::vector<char> out;
+        std::string err;
+        bool done = false;
+    };
+    FILE *f = nullptr;
+    bool eof = false;
+    std::string read_err;
+    std::deque<std::shared_ptr<Job>> order;             /* jobs in file order, oldest first */
+    std::deque<std::shared_ptr<Job>> todo;              /* not yet taken by a pool thread */
+    std::vector<std::thread> pool;
+    std::mutex mu;
+    std::condition_variable cv_todo, cv_done;
+    bool stop = false;
+
+    /* true if the file starts with a BGZF block header */
+    static bool probe(const char *path)
+    {
+        FILE *g = fopen(path, "rb");
+        if (!g) return false;
+        unsigned char h[18];
+        const bool ok = fread(h, 1, 18, g) == 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) &&
+                        h[10] == 6 && h[11] == 0 && h[12] == 'B' && h[13] == 'C' && h[14] == 2 && h[15] == 0;
+        fclose(g);
+        return ok;
+    }
+    BgzfSource(const char *path, int n_threads)
+    {
+        f = fopen(path, "rb");
+        if (!f) { read_err = "cannot open file"; eof = true; return; }
+        setvbuf(f, nullptr, _IOFBF, 4u << 20);
+        for (int t = 0; t < n_threads; t++) pool.emplace_back([this]() { work(); });
+    }
+    ~BgzfSource()
+    {
+        { std::lock_guard<std::mutex> g(mu); stop = true; }
+        cv_todo.notify_all();
+        for (auto &t : pool) t.join();
+        if (f) fclose(f);
+    }
+    void work()
+    {
+        for (;;) {
+            std::shared_ptr<Job> j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_todo.wait(lk, [this]() { return stop || !todo.empty(); });
+                if (stop) return;
+                j = todo.front(); todo.pop_front();
+            }
+            size_t total = 0;
+            for (uint32_t n : j->isize) total += n;
+            j->out.resize(total);
+            size_t in_pos = 0, out_pos = 0;
+            for (size_t b = 0; b < j->clen.size() && j->err.empty(); b++) {
+                z_stream zs;
+                memset(&zs, 0, sizeof zs);
+                if (inflateInit2(&zs, -15) != Z_OK) { j->err = "inflateInit2 failed"; break; }
+                zs.next_in = j->raw.data() + in_pos; zs.avail_in = j->clen[b];
+                zs.next_out = (Bytef *)j->out.data() + out_pos; zs.avail_out = j->isize[b];
+                const int r = inflate(&zs, Z_FINISH);
+                inflateEnd(&zs);
+                if (r != Z_STREAM_END || zs.avail_out != 0) { j->err = "corrupt BGZF block"; break; }
+                if (j->isize[b] && (uint32_t)crc32(0L, (const Bytef *)j->out.data() + out_pos, j->isize[b]) != j->crc[b]) {
+                    j->err = "BGZF block fails its CRC"; break;
+                }
+                in_pos += j->clen[b]; out_pos += j->isize[b];
+            }
+            { std::lock_guard<std::mutex> g(mu); j->done = true; }
+            cv_done.notify_all();
+        }
+    }
+    /* the next ~1 MiB of blocks as a job; nullptr at the end of the file or on a malformed header (read_err set) */
+    std::shared_ptr<Job> read_job()
+    {
+        if (eof) return nullptr;
+        auto j = std::make_shared<Job>();
+        while (j->raw.size() < (1u << 20)) {
+            unsigned char h[12];
+            const size_t got = fread(h, 1, 12, f);
+            if (got == 0) { eof = true; break; }
+            if (got != 12 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { read_err = "not a BGZF block header"; eof = true; break; }
+            const unsigned xlen = h[10] | (h[11] << 8);
+            unsigned char extra[65536];
+            if (fread(extra, 1, xlen, f) != xlen) { read_err = "truncated BGZF block"; eof = true; break; }
+            int bsize = -1;
+            for (unsigned o = 0; o + 4 <= xlen;) {
+                const unsigned slen = extra[o + 2] | (extra[o + 3] << 8);
+                if (extra[o] == 'B' && extra[o + 1] == 'C' && slen == 2 && o + 6 <= xlen) bsize = extra[o + 4] | (extra[o + 5] << 8);
+                o += 4 + slen;
+            }
+            const long clen = (long)bsize - (long)xlen - 19;
+            if (bsize < 0 || clen < 0) { read_err = "BGZF block without a size field"; eof = true; break; }
+            const size_t at = j->raw.size();
+            j->raw.resize(at + (size_t)clen);
+            unsigned char tr[8];
+            if (fread(j->raw.data() + at, 1, (size_t)clen, f) != (size_t)clen || fread(tr, 1, 8, f) != 8) {
+                read_err = "truncated BGZF block"; eof = true; j->raw.resize(at); break;
+            }
+            j->clen.push_back((uint32_t)clen);
+            j->crc.push_back(tr[0] | (tr[1] << 8) | (tr[2] << 16) | ((uint32_t)tr[3] << 24));
+            j->isize.push_back(tr[4] | (tr[5] << 8) | (tr[6] << 16) | ((uint32_t)tr[7] << 24));
+        }
+        return j->clen.empty() ? nullptr : j;
+    }
+    /* appends the next job's bytes to buf at *end (growing buf); false at the end of the file or on error (*err set) */
+    bool next(std::vector<char> &buf, size_t *end, std::string *err)
+    {
+        for (;;) {
+            while (order.size() < 2 * pool.size() + 1) {         /* keep the pool busy */
+                auto j = read_job();
+                if (!j) break;
+                { std::lock_guard<std::mutex> g(mu); todo.push_back(j); }
+                order.push_back(j);
+                cv_todo.notify_one();
+            }
+            if (order.empty()) { *err = read_err; return false; }
+            auto j = order.front();
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_done.wait(lk, [&]() { return j->done; });
+            }
+            order.pop_front();
+            if (!j->err.empty()) { *err = j->err; return false; }
+            if (j->out.empty()) continue;                         /* only empty blocks (the end-of-file marker) */
+            if (buf.size() < *end + j->out.size()) buf.resize(std::max(buf.size() * 2, *end + j->out.size()));
+            memcpy(buf.data() + *end, j->out.data(), j->out.size());
+            *end += j->out.size();
+            return true;
+        }
+    }
+};
+
 /* One file of the list: its own thread inflates AND parses it into a bounded queue of record batches. */
 struct FileStream {
     static constexpr size_t BATCH_BYTES = 2u << 20;
@@ -55,12 +198,17 @@ struct FileStream {
     std::string error;              /* set before finished */
 
     /* producer-private: buffered line reader over the gzip stream */
+    int inflate_threads = 1;        /* > 1: a BGZF file is inflated by a pool of that many threads */
+    std::unique_ptr<BgzfSource> bgzf;
     gzFile gz = nullptr;
     std::vector<char> buf;
     size_t pos = 0, end = 0;
     std::string zerr;
 
-    FileStream(const std::string &p, bool fq, size_t d) : depth(d), path(p), fastq(fq) { th = std::thread([this]() { produce(); }); }
+    FileStream(const std::string &p, bool fq, size_t d, int inflate_thr = 1) : depth(d), path(p), fastq(fq), inflate_threads(inflate_thr)
+    {
+        th = std::thread([this]() { produce(); });
+    }
     ~FileStream()
     {
         { std::lock_guard<std::mutex> g(mu); cancel = true; }
@@ -70,6 +218,7 @@ struct FileStream {
     void finish(const std::string &err)
     {
         if (gz) { gzclose(gz); gz = nullptr; }
+        bgzf.reset();
         { std::lock_guard<std::mutex> g(mu); error = err; finished = true; }
         cv.notify_all();
     }
@@ -103,10 +252,21 @@ struct FileStream {
     {
         if (pos > 0 && pos < end) memmove(buf.data(), buf.data() + pos, end - pos);
         end -= pos; pos = 0;
+        if (bgzf) {
+            std::string e;
+            if (bgzf->next(buf, &end, &e)) return true;
+            if (!e.empty()) zerr = path + ": " + e;
+            return false;
+        }
         if (end == buf.size()) buf.resize(buf.size() * 2);
         const int got = gzread(gz, buf.data() + end, (unsigned)std::min<size_t>(buf.size() - end, 1u << 30));
         if (got < 0) { int e; zerr = path + ": " + gzerror(gz, &e); return false; }
-        if (got == 0) return false;
+        if (got == 0) {                 /* end of file -- or a stream that stops in the middle of a member */
+            int e = Z_OK;
+            const char *msg = gzerror(gz, &e);
+            if (e == Z_BUF_ERROR || e == Z_DATA_ERROR) zerr = path + ": " + (msg && *msg ? msg : "truncated gzip stream");
+            return false;
+        }
         end += (size_t)got;
         return true;
     }
@@ -134,9 +294,12 @@ struct FileStream {
     }
     void produce()
     {
-        gz = gzopen(path.c_str(), "rb");
-        if (!gz) { finish("cannot open " + path); return; }
-        gzbuffer(gz, 1u << 20);
+        if (inflate_threads > 1 && BgzfSource::probe(path.c_str())) bgzf.reset(new BgzfSource(path.c_str(), inflate_threads));
+        else {
+            gz = gzopen(path.c_str(), "rb");
+            if (!gz) { finish("cannot open " + path); return; }
+            gzbuffer(gz, 1u << 20);
+        }
         buf.resize(4u << 20);
         Batch bt;
         std::string pending;            /* FASTA: header of the record that follows the one just finished */
@@ -206,6 +369,7 @@ struct ntl_reader {
     size_t file_idx = 0;
     std::vector<std::unique_ptr<FileStream>> streams;   /* one slot per path; created up to `ahead` files early */
     size_t started = 0, ahead = 8;
+    int inflate_threads = 1;        /* per file: cores / files that are open side by side (BGZF files only) */
     size_t budget_mb = 2048;        /* parsed records the file threads may hold in total: whole files of a typical run
                                        fit, so that the files really are inflated side by side */
     Batch bt;                       /* batch being handed out */
@@ -228,7 +392,8 @@ struct ntl_reader {
             if (streams.size() < paths.size()) streams.resize(paths.size());
             for (; started < paths.size() && started < file_idx + ahead; started++)
                 streams[started].reset(new FileStream(paths[started], fastq,
-                                                      std::max<size_t>(4, (budget_mb << 20) / ahead / FileStream::BATCH_BYTES)));
+                                                      std::max<size_t>(4, (budget_mb << 20) / ahead / FileStream::BATCH_BYTES),
+                                                      inflate_threads));
             std::string e;
             bt = Batch(); bt_rec = 0;
             if (!streams[file_idx]->pop(&bt, &e)) {
@@ -302,6 +467,13 @@ extern "C" int ntl_reader_open(ntl_reader **out, const char *const *paths, int32
     r->ahead = std::min<size_t>(16, std::max<size_t>(2, std::thread::hardware_concurrency()));
     if (const char *a = getenv("NTL_READER_FILES")) { const int v = atoi(a); if (v >= 1 && v <= 64) r->ahead = (size_t)v; }
     if (const char *a = getenv("NTL_READER_MB")) { const int v = atoi(a); if (v >= 16 && v <= (1 << 20)) r->budget_mb = (size_t)v; }
+    {   /* cores left over when the list is shorter than the core count go to the inside of BGZF files */
+        const size_t cores = std::max<size_t>(1, std::thread::hardware_concurrency());
+        const size_t side_by_side = std::min<size_t>(r->ahead, (size_t)n_paths);
+        /* two cores stay with the line parser and the consumer of the chunks */
+        r->inflate_threads = (int)std::min<size_t>(32, std::max<size_t>(1, (cores > 3 ? cores - 2 : cores) / side_by_side));
+        if (const char *a = getenv("NTL_READER_BGZF_THREADS")) { const int v = atoi(a); if (v >= 1 && v <= 64) r->inflate_threads = v; }
+    }
     *out = r;
     return NTL_OK;
 }

@@ -166,3 +166,61 @@ def test_varying_nrec_never_drops_records(tmp_path):
             got_names.append(nraw[int(noff[i]):int(noff[i + 1])].decode())
     L.ntl_reader_close(h)
     assert got_names == names and got_seqs == seqs
+
+
+def _bgzf(data: bytes, block: int = 60000, level: int = 6) -> bytes:
+    """bgzip's container: gzip members of at most 64 KiB, each with a "BC" extra field holding its size - 1, then the
+    empty end-of-file block."""
+    import struct
+    import zlib
+    out = []
+    for k in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if k is None else data[k:k + block]
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        cdata = c.compress(chunk) + c.flush()
+        bsize = len(cdata) + 25                                        # header 12 + extra 6 + cdata + crc 4 + isize 4 - 1
+        out.append(b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize) +
+                   cdata + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("threads", ["1", "4"])
+def test_bgzf_files_are_inflated_by_a_pool(tmp_path, monkeypatch, threads):
+    """A BGZF (bgzip) file is a chain of small gzip members that announce their size: with NTL_READER_BGZF_THREADS > 1
+    its blocks are inflated by a pool of threads (1: zlib's gzread walks the members).  Same records either way, for
+    FASTQ and multi-line FASTA, blocks cutting lines anywhere; gzip reads it too (it IS gzip); a corrupt block or a
+    truncated file is an error, not silence."""
+    from nanotel_b200.nanotel import NativeReader, iter_chunks
+    monkeypatch.setenv("NTL_READER_BGZF_THREADS", threads)
+    rng = np.random.default_rng(21)
+    recs, fq, fa = [], [], []
+    for i in range(700):
+        L = int(rng.integers(1, 30000 if i % 50 == 0 else 3000))
+        n, s = "read%04d some description" % i, bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), L))
+        recs.append((n, s))
+        fq.append(b"@" + n.encode() + b"\n" + s + b"\n+\n" + b"I" * L + b"\n")
+        fa.append(b">" + n.encode() + b"\n" + b"\n".join(s[k:k + 70] for k in range(0, L, 70)) + b"\n")
+    fq, fa = b"".join(fq), b"".join(fa)
+    assert gzip.decompress(_bgzf(fq)) == fq                              # the container is what it claims to be
+    for fmt, text in (("fastq", fq), ("fasta", fa)):
+        for block in (60000, 4097):
+            p = tmp_path / ("b%d.%s.gz" % (block, fmt))
+            p.write_bytes(_bgzf(text, block))
+            for nrec in (100, 0):
+                got = _native([str(p)], fmt, nrec)
+                assert [r for c in got for r in c] == recs
+                assert got == list(iter_chunks([str(p)], fmt, nrec))
+    # a list that mixes BGZF, plain gzip and uncompressed files
+    p1, p2, p3 = tmp_path / "m1.fastq.gz", tmp_path / "m2.fastq.gz", tmp_path / "m3.fastq"
+    p1.write_bytes(_bgzf(fq)); p2.write_bytes(gzip.compress(fq)); p3.write_bytes(fq)
+    got = _native([str(p1), str(p2), str(p3)], "fastq", 512)
+    assert [r for c in got for r in c] == recs * 3
+    # corruption inside a block's deflate data, and a file cut in the middle of a block
+    good = _bgzf(fq)
+    bad = bytearray(good); bad[len(bad) // 2] ^= 0x55
+    (tmp_path / "bad.fastq.gz").write_bytes(bytes(bad))
+    with pytest.raises(ValueError):
+        list(NativeReader([str(tmp_path / "bad.fastq.gz")], "fastq", 0))
+    (tmp_path / "cut.fastq.gz").write_bytes(good[:len(good) // 2])
+    with pytest.raises(ValueError):
+        list(NativeReader([str(tmp_path / "cut.fastq.gz")], "fastq", 0))
