@@ -101,7 +101,8 @@ typedef struct {
     uint8_t        *cls[3];            /* per track: class byte of every span (blocks per span <= 8), or NULL       */
     int64_t         cls_base;          /* entry of span 0 of this arena inside a track's class plane              */
     int32_t         blk_thr;           /* a block's class bit: count >= blk_thr                                    */
-    int32_t         pad;
+    int32_t         pad;               /* always 0: the kernel derives a multiplier of 1 from it that the compiler
+                                          cannot fold (ntl_mad1: additions moved to the FMA pipe)                    */
 } ntl_scan_args;
 
 /* Arguments of the filter (K4), generic scan and locate (K3) kernels. */
