@@ -250,3 +250,14 @@ def test_analysis_post_processing(tmp_path):
     # nothing survives: R prints NA and NaN
     got0, _ = run_analysis(df.iloc[:0], str(tmp_path), "empty")
     assert len(got0) == 0 and "NA" in open(tmp_path / "empty_results.txt").read()
+
+
+def test_host_memory_probe_runs_without_a_device():
+    """ntl_host_read_gbs (the packer's ceiling that bench.py reports beside the packer's rate): plain reads and the
+    read + quarter-size write pattern both return a positive rate; bad arguments return 0."""
+    from nanotel_b200 import _lib
+    L = _lib.load()
+    a = np.random.default_rng(3).integers(65, 85, 32 << 20, dtype=np.uint8)
+    assert L.ntl_host_read_gbs(a.ctypes.data, a.nbytes, 2, 2) > 0.05
+    assert L.ntl_host_read_gbs(a.ctypes.data, a.nbytes, 2, -2) > 0.05
+    assert L.ntl_host_read_gbs(None, a.nbytes, 2, 2) == 0.0 and L.ntl_host_read_gbs(a.ctypes.data, 0, 2, 2) == 0.0
