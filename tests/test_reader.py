@@ -224,3 +224,24 @@ def test_bgzf_files_are_inflated_by_a_pool(tmp_path, monkeypatch, threads):
     (tmp_path / "cut.fastq.gz").write_bytes(good[:len(good) // 2])
     with pytest.raises(ValueError):
         list(NativeReader([str(tmp_path / "cut.fastq.gz")], "fastq", 0))
+
+
+def test_views_instead_of_copies(tmp_path):
+    """copy=False (the chunk loop's mode): the sequence buffer of a chunk is a view of the reader's own buffer, valid
+    until the next chunk is requested; consumed chunk by chunk it yields the same records as the copying mode."""
+    from nanotel_b200.nanotel import NativeReader
+    rng = np.random.default_rng(8)
+    p = tmp_path / "v.fastq.gz"
+    recs = []
+    with gzip.open(p, "wb") as f:
+        for i in range(900):
+            L = int(rng.integers(1, 4000))
+            n, s = "v%03d" % i, bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), L))
+            recs.append((n, s))
+            f.write(b"@" + n.encode() + b"\n" + s + b"\n+\n" + b"I" * L + b"\n")
+    got = []
+    for names, buf, off in NativeReader([str(p)], "fastq", 64, copy=False):
+        assert not buf.flags["OWNDATA"]
+        got += [(names[i], buf[int(off[i]):int(off[i + 1])].tobytes()) for i in range(len(names))]
+    assert got == recs
+    assert [r for c in _native([str(p)], "fastq", 64) for r in c] == recs
