@@ -159,6 +159,9 @@ class _LazyChunk:
     def __getitem__(self, i):
         return self.names[i], self.buf[int(self.off[i]):int(self.off[i + 1])].tobytes()
 
+    def length(self, i) -> int:
+        return int(self.off[i + 1] - self.off[i])
+
 
 def _tokens(p) -> List[str]:
     if p is None:
@@ -172,9 +175,10 @@ def _rows_from_results(reads: Sequence[Read], res: np.ndarray, serial: np.ndarra
                        n_tracks: int):
     """One summary row per kept read (analyze_read's add_row, NanoTel.R:1923-1974), in `order`."""
     rows = []
+    lazy = isinstance(reads, _LazyChunk)                     # a reader chunk knows the lengths without copying a read
     for i in order:
         r = res[i]
-        row = [int(serial[i]), reads[i][0], len(reads[i][1])]
+        row = [int(serial[i]), reads.names[i], reads.length(i)] if lazy else [int(serial[i]), reads[i][0], len(reads[i][1])]
         for t in range(n_tracks):
             tr = r["track"][t]
             if int(tr["start"]) == -1:                       # NanoTel.R:1926-1931: NA for this track
