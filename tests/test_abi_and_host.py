@@ -261,3 +261,19 @@ def test_host_memory_probe_runs_without_a_device():
     assert L.ntl_host_read_gbs(a.ctypes.data, a.nbytes, 2, 2) > 0.05
     assert L.ntl_host_read_gbs(a.ctypes.data, a.nbytes, 2, -2) > 0.05
     assert L.ntl_host_read_gbs(None, a.nbytes, 2, 2) == 0.0 and L.ntl_host_read_gbs(a.ctypes.data, 0, 2, 2) == 0.0
+
+
+def test_summary_rows_from_a_reader_chunk_equal_rows_from_a_list():
+    """_rows_from_results on a reader chunk (lengths from the offsets, no read is copied) = on a list of (name, seq)."""
+    from nanotel_b200 import _lib
+    from nanotel_b200 import nanotel as N
+    res = np.zeros(3, _lib.RESULT_DTYPE)
+    res["track"]["start"][:] = [[5, -1, 0], [1, 2, 0], [7, 8, 0]]
+    res["track"]["end"][:] = [[50, 0, 0], [10, 20, 0], [70, 80, 0]]
+    res["track"]["density"][:] = 0.5
+    buf, off = np.frombuffer(b"ACGTACGTAAACG", np.uint8), np.array([0, 4, 8, 13])
+    chunk = N._LazyChunk(["a", "b x", "c"], buf, off)
+    lst = [("a", b"ACGT"), ("b x", b"ACGT"), ("c", b"AAACG")]
+    serial = np.array([1, 2, 3])
+    assert N._rows_from_results(chunk, res, serial, [2, 0], 2) == N._rows_from_results(lst, res, serial, [2, 0], 2)
+    assert N._rows_from_results(chunk, res, serial, [2, 0], 2)[0][:3] == [3, "c", 5]
